@@ -1,0 +1,262 @@
+/* sylver_b200.h -- C ABI of libsylver_b200.so
+ *
+ * Drop-in boundary for the numeric-factorization path of NLAFET/SyLVER, rebuilt
+ * for NVIDIA B200 (sm_100a).  Three groups of entry points:
+ *
+ *  (1) the public SyLVER C API (binary compatible with the reference's
+ *      include/sylver/sylver.h:19-123: same struct layouts, same symbol names),
+ *  (2) the internal Fortran->C++ seam the reference's Fortran driver calls
+ *      (src/SymbolicTree.cxx:109-137, src/NumericTree.cxx:26-136,
+ *      src/NumericTreePosdef.cxx:19-83): a maintainer who keeps the Fortran
+ *      analyse/factorize drivers links these instead of the StarPU engine,
+ *  (3) sylver_b200_* helpers (introspection, dense single-front drivers,
+ *      micro-benchmarks) used by the tests, bench.py and INTEGRATION.md.
+ *
+ * Conventions (reference: src/interfaces/C/sylver_ciface.F90:374-631):
+ *  - A is symmetric, lower triangle in CSC, `long` column pointers, 1-based
+ *    ptr/row/order regardless of options.array_base (the reference ignores it).
+ *  - Errors are reported in inform->flag (<0 error, >0 warning); nothing throws.
+ *  - No CPU fallback exists: without a CUDA device (sm_100) every numeric entry
+ *    point sets inform->flag = SYLVER_ERROR_CUDA_UNKNOWN (-51).
+ *  - `val` passed to spldlt_factorize / the numeric-tree seam may be a host or a
+ *    device pointer (detected with cudaPointerGetAttributes).
+ */
+#ifndef SYLVER_B200_H
+#define SYLVER_B200_H
+
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------
+ * (1) Public API -- replaces include/sylver/sylver.h
+ * ------------------------------------------------------------------------- */
+
+/* Layout of reference sylver_inform_t (include/sylver/sylver.h:19-37). */
+typedef struct {
+   int flag;
+   int matrix_dup;
+   int matrix_missing_diag;
+   int matrix_outrange;
+   int matrix_rank;
+   int maxdepth;
+   int maxfront;
+   int num_delay;
+   long num_factor;
+   long num_flops;
+   int num_neg;
+   int num_sup;
+   int num_two;
+   int stat;
+   int cuda_error;
+   int cublas_error;
+   char unused[80];
+} sylver_inform_t;
+
+/* Layout of reference sylver_options_t (include/sylver/sylver.h:39-71);
+ * defaults from src/sylver_datatypes_mod.F90:97-198. */
+typedef struct {
+   int array_base;
+   int print_level;
+   int unit_diagnostics;
+   int unit_error;
+   int unit_warning;
+   int ordering;              /* 0 = user order (the only one implemented here) */
+   int nemin;                 /* 32 */
+   bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
+   long min_gpu_work;
+   int scaling;               /* <=0: none / user supplied */
+   int pivot_method;          /* 1 APP aggressive, 2 APP block, 3 TPP */
+   double small;              /* 1e-20 */
+   double u;                  /* 0.01 */
+   long small_subtree_threshold;
+   int nb;                    /* 256 */
+   int cpu_topology;
+   bool action;               /* true: continue on singularity with a warning */
+   bool use_gpu;
+   double gpu_perf_coeff;
+   int failed_pivot_method;   /* 1 TPP on failed columns, 2 pass to parent */
+   int scheduler;
+} sylver_options_t;
+
+/* error / warning codes, src/sylver_datatypes_mod.F90:13-45 */
+enum {
+   SYLVER_SUCCESS = 0,
+   SYLVER_ERROR_CALL_SEQUENCE = -1,
+   SYLVER_ERROR_A_N_OOR = -2,
+   SYLVER_ERROR_A_PTR = -3,
+   SYLVER_ERROR_A_ALL_OOR = -4,
+   SYLVER_ERROR_SINGULAR = -5,
+   SYLVER_ERROR_NOT_POS_DEF = -6,
+   SYLVER_ERROR_PTR_ROW = -7,
+   SYLVER_ERROR_ORDER = -8,
+   SYLVER_ERROR_VAL = -9,
+   SYLVER_ERROR_X_SIZE = -10,
+   SYLVER_ERROR_JOB_OOR = -11,
+   SYLVER_ERROR_NOT_LLT = -13,
+   SYLVER_ERROR_NOT_LDLT = -14,
+   SYLVER_ERROR_NO_SAVED_SCALING = -15,
+   SYLVER_ERROR_ALLOCATION = -50,
+   SYLVER_ERROR_CUDA_UNKNOWN = -51,
+   SYLVER_ERROR_CUBLAS_UNKNOWN = -52,
+   SYLVER_ERROR_UNIMPLEMENTED = -98,
+   SYLVER_ERROR_UNKNOWN = -99,
+   SYLVER_WARNING_ANAL_SINGULAR = 6,
+   SYLVER_WARNING_FACT_SINGULAR = 7
+};
+
+/* sylver.h:73  -- ncpu is accepted and ignored; ngpu = number of B200s this
+ * process may use (the one-process-per-GPU launcher passes 1). */
+void sylver_init(int ncpu, int ngpu);
+/* sylver.h:75 */
+void sylver_finalize(void);
+/* sylver.h:77 */
+void sylver_default_options(sylver_options_t *options);
+/* sylver.h:79-83 ; options->ordering must be 0 (order supplied), order is
+ * overwritten with the final elimination order. */
+void spldlt_analyse(int n, int *order, long const *ptr, int const *row,
+                    double const *val, void **akeep, bool check,
+                    sylver_options_t const *options, sylver_inform_t *inform);
+/* sylver.h:95-98 */
+void spldlt_factorize(bool posdef, long const *ptr, int const *row,
+                      double const *val, double *scale, void *akeep, void **fkeep,
+                      sylver_options_t const *options, sylver_inform_t *inform);
+/* sylver.h:100-102 ; job: 0 all, 1 fwd, 2 diag, 3 bwd, 4 diag+bwd */
+void spldlt_solve(int job, int nrhs, double *x, int ldx, void *akeep, void *fkeep,
+                  sylver_options_t const *options, sylver_inform_t *inform);
+/* sylver.h:121,123 */
+void spldlt_free_akeep(void **akeep);
+void spldlt_free_fkeep(void **fkeep);
+
+/* ---------------------------------------------------------------------------
+ * (2) Internal seam -- replaces the StarPU engine behind the Fortran driver
+ * ------------------------------------------------------------------------- */
+
+/* Interoperable option / inform subsets, src/sylver_ciface.hxx:39-87 and
+ * src/sylver_ciface_mod.F90:9-32. */
+typedef struct {
+   int print_level;
+   bool action;
+   double small;
+   double u;
+   double multiplier;
+   long small_subtree_threshold;
+   int nb;
+   int pivot_method;
+   int failed_pivot_method;
+   int cpu_topology;
+} sylver_options_c;
+
+typedef struct {
+   int flag;
+   int num_delay;
+   int num_neg;
+   int num_two;
+   int num_zero;
+   int maxfront;
+   int not_first_pass;
+   int not_second_pass;
+} sylver_inform_c;
+
+/* src/SymbolicTree.cxx:109-137.  All index arrays are 1-based and BORROWED
+ * only during the call (the device plan copies what it needs).  subtrees /
+ * small / contrib_dest / exec_loc may be NULL (nsubtrees must then be 0: the
+ * B200 engine factorizes every front itself). */
+void *spldlt_create_symbolic_tree(void *akeep, int n, int nnodes, int const *sptr,
+                                  int const *sparent, long const *rptr,
+                                  int const *rlist, long const *nptr,
+                                  long const *nlist, int nsubtrees,
+                                  int const *subtrees, int const *small,
+                                  int const *contrib_dest, int const *exec_loc);
+void spldlt_destroy_symbolic_tree(void *symbolic_tree);
+
+/* src/NumericTree.cxx:26-44: factorization happens inside, synchronous. */
+void *spldlt_create_numeric_tree_dbl(bool posdef, void *fkeep, void *symbolic_tree,
+                                     double *aval, const double *scaling,
+                                     void **child_contrib,
+                                     sylver_options_c *options,
+                                     sylver_inform_c *stats);
+/* src/NumericTreePosdef.cxx:19-35 */
+void *spldlt_create_numeric_tree_posdef_dbl(void *fkeep, void *symbolic_tree,
+                                            double *aval, const double *scaling,
+                                            void **child_contrib,
+                                            sylver_options_c *options,
+                                            sylver_inform_c *stats);
+void spldlt_destroy_numeric_tree_dbl(bool posdef, void *tree);
+void spldlt_destroy_numeric_tree_posdef_dbl(void *tree);
+
+/* src/NumericTree.cxx:54-136 (x already permuted to elimination order; host or
+ * device pointer).  Return a Flag (0 success). */
+int spldlt_tree_solve_fwd_dbl(bool posdef, void const *tree, int nrhs, double *x, int ldx);
+int spldlt_tree_solve_bwd_dbl(bool posdef, void const *tree, int nrhs, double *x, int ldx);
+int spldlt_tree_solve_diag_dbl(bool posdef, void const *tree, int nrhs, double *x, int ldx);
+int spldlt_tree_solve_diag_bwd_dbl(bool posdef, void const *tree, int nrhs, double *x, int ldx);
+/* src/NumericTreePosdef.cxx:44-83 */
+int spldlt_tree_solve_fwd_posdef_dbl(void const *tree, int nrhs, double *x, int ldx);
+int spldlt_tree_solve_bwd_posdef_dbl(void const *tree, int nrhs, double *x, int ldx);
+
+/* ---------------------------------------------------------------------------
+ * (3) sylver_b200_* helpers
+ * ------------------------------------------------------------------------- */
+
+/* Library / device introspection. Returns number of visible CUDA devices
+ * (0 when none; never fails). */
+int sylver_b200_device_count(void);
+const char *sylver_b200_version(void);
+
+/* Symbolic introspection of an akeep (for bit-exact parity tests).  Each
+ * pointer receives a borrowed pointer valid until spldlt_free_akeep. */
+typedef struct {
+   int n;
+   int nnodes;
+   int const *sptr;      /* nnodes+1 */
+   int const *sparent;   /* nnodes   */
+   long const *rptr;     /* nnodes+1 */
+   int const *rlist;     /* rptr[nnodes]-1 */
+   long const *nptr;     /* nnodes+1 */
+   long const *nlist;    /* 2*(nptr[nnodes]-1) */
+   int const *order;     /* n */
+   int const *invp;      /* n */
+   long num_factor;
+   long num_flops;
+} sylver_b200_symbolic_view;
+int sylver_b200_akeep_view(void *akeep, sylver_b200_symbolic_view *view);
+
+/* Per-edge assembly maps derived at symbolic-tree creation:
+ * for node c (0-based) cmap[cptr[c] .. cptr[c+1]) gives, for each contribution
+ * row of c, its 0-based local row index in the parent front.  Borrowed. */
+int sylver_b200_symbolic_tree_cmap(void *symbolic_tree, long const **cptr,
+                                   int const **cmap);
+
+/* Timings of the last factorization on an fkeep/numeric tree (seconds):
+ * out[0]=total device time (CUDA events), out[1]=H2D of aval, out[2]=host
+ * wall time of the call, out[3]=kernel launches issued. */
+int sylver_b200_numeric_tree_timings(void const *tree, double *out4);
+void *sylver_b200_fkeep_tree(void *fkeep);
+
+/* Dense single front drivers (reference harness shape:
+ * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).
+ * a: m x n column-major panel (lda >= m), host memory, overwritten by L;
+ * d: 2*n (D^-1 in the reference's storage convention), perm: n (in: 1-based
+ * labels, out: permuted), contrib: (m-n)^2 (ld m-n) receives the Schur
+ * complement.  Returns nelim (>=0) or a negative SYLVER_ERROR_*.
+ * ms_out (may be NULL) receives device milliseconds of the factorization. */
+int sylver_b200_factor_front_posdef(int m, int n, double *a, int lda,
+                                    double *contrib, int nb, float *ms_out);
+int sylver_b200_factor_front_indef(int m, int n, int *perm, double *a, int lda,
+                                   double *d, double *contrib,
+                                   sylver_options_c const *options,
+                                   sylver_inform_c *stats, float *ms_out);
+
+/* Micro-benchmarks run on the current device; return achieved TFLOP/s or GB/s
+ * (negative on error).  kind 0: register-resident DMMA issue peak,
+ * 1: our tiled DMMA SYRK/GEMM update kernel on an n x n x k problem. */
+double sylver_b200_bench_dmma(int kind, int n, int k, int iters);
+double sylver_b200_bench_copy(long nbytes, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYLVER_B200_H */

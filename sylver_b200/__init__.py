@@ -1,0 +1,250 @@
+"""sylver_b200 -- B200-native numeric factorization behind SyLVER's C ABI.
+
+This package is a thin ctypes binding over ``libsylver_b200.so`` (built in-tree
+by :mod:`sylver_b200.build`).  The Python layer mirrors the reference's C API
+one to one (``spldlt_analyse / spldlt_factorize / spldlt_solve``,
+/root/reference/include/sylver/sylver.h:73-123); all numeric work happens in
+the hand-written sm_100a kernels inside the shared library.  There is no CPU
+fallback: numeric calls on a machine without a CUDA device return
+``flag == -51`` and :func:`require_gpu` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsylver_b200.so")
+
+
+class Inform(C.Structure):
+    _fields_ = [("flag", C.c_int), ("matrix_dup", C.c_int), ("matrix_missing_diag", C.c_int),
+                ("matrix_outrange", C.c_int), ("matrix_rank", C.c_int), ("maxdepth", C.c_int),
+                ("maxfront", C.c_int), ("num_delay", C.c_int), ("num_factor", C.c_long),
+                ("num_flops", C.c_long), ("num_neg", C.c_int), ("num_sup", C.c_int),
+                ("num_two", C.c_int), ("stat", C.c_int), ("cuda_error", C.c_int),
+                ("cublas_error", C.c_int), ("unused", C.c_char * 80)]
+
+
+class Options(C.Structure):
+    _fields_ = [("array_base", C.c_int), ("print_level", C.c_int), ("unit_diagnostics", C.c_int),
+                ("unit_error", C.c_int), ("unit_warning", C.c_int), ("ordering", C.c_int),
+                ("nemin", C.c_int), ("prune_tree", C.c_bool), ("min_gpu_work", C.c_long),
+                ("scaling", C.c_int), ("pivot_method", C.c_int), ("small", C.c_double),
+                ("u", C.c_double), ("small_subtree_threshold", C.c_long), ("nb", C.c_int),
+                ("cpu_topology", C.c_int), ("action", C.c_bool), ("use_gpu", C.c_bool),
+                ("gpu_perf_coeff", C.c_double), ("failed_pivot_method", C.c_int),
+                ("scheduler", C.c_int)]
+
+
+class OptionsC(C.Structure):
+    """sylver::options_c (reference src/sylver_ciface.hxx:39-55)."""
+    _fields_ = [("print_level", C.c_int), ("action", C.c_bool), ("small", C.c_double),
+                ("u", C.c_double), ("multiplier", C.c_double),
+                ("small_subtree_threshold", C.c_long), ("nb", C.c_int),
+                ("pivot_method", C.c_int), ("failed_pivot_method", C.c_int),
+                ("cpu_topology", C.c_int)]
+
+
+class InformC(C.Structure):
+    """sylver::inform_c (reference src/sylver_ciface.hxx:72-87)."""
+    _fields_ = [("flag", C.c_int), ("num_delay", C.c_int), ("num_neg", C.c_int),
+                ("num_two", C.c_int), ("num_zero", C.c_int), ("maxfront", C.c_int),
+                ("not_first_pass", C.c_int), ("not_second_pass", C.c_int)]
+
+
+class SymbolicView(C.Structure):
+    _fields_ = [("n", C.c_int), ("nnodes", C.c_int), ("sptr", C.POINTER(C.c_int)),
+                ("sparent", C.POINTER(C.c_int)), ("rptr", C.POINTER(C.c_long)),
+                ("rlist", C.POINTER(C.c_int)), ("nptr", C.POINTER(C.c_long)),
+                ("nlist", C.POINTER(C.c_long)), ("order", C.POINTER(C.c_int)),
+                ("invp", C.POINTER(C.c_int)), ("num_factor", C.c_long), ("num_flops", C.c_long)]
+
+
+_lib = None
+
+# every symbol include/sylver_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "sylver_init", "sylver_finalize", "sylver_default_options", "spldlt_analyse",
+    "spldlt_factorize", "spldlt_solve", "spldlt_free_akeep", "spldlt_free_fkeep",
+    "spldlt_create_symbolic_tree", "spldlt_destroy_symbolic_tree",
+    "spldlt_create_numeric_tree_dbl", "spldlt_create_numeric_tree_posdef_dbl",
+    "spldlt_destroy_numeric_tree_dbl", "spldlt_destroy_numeric_tree_posdef_dbl",
+    "spldlt_tree_solve_fwd_dbl", "spldlt_tree_solve_bwd_dbl", "spldlt_tree_solve_diag_dbl",
+    "spldlt_tree_solve_diag_bwd_dbl", "spldlt_tree_solve_fwd_posdef_dbl",
+    "spldlt_tree_solve_bwd_posdef_dbl", "sylver_b200_device_count", "sylver_b200_version",
+    "sylver_b200_akeep_view", "sylver_b200_symbolic_tree_cmap", "sylver_b200_numeric_tree_timings",
+    "sylver_b200_fkeep_tree", "sylver_b200_factor_front_posdef", "sylver_b200_factor_front_indef",
+    "sylver_b200_bench_dmma", "sylver_b200_bench_copy",
+]
+
+
+def lib() -> C.CDLL:
+    """Load libsylver_b200.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m sylver_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU/PyTorch fallback for the factorization path.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, lp, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_double)
+    L.sylver_init.argtypes = [C.c_int, C.c_int]
+    L.sylver_default_options.argtypes = [C.POINTER(Options)]
+    L.spldlt_analyse.argtypes = [C.c_int, vp, vp, vp, vp, C.POINTER(vp), C.c_bool,
+                                 C.POINTER(Options), C.POINTER(Inform)]
+    L.spldlt_factorize.argtypes = [C.c_bool, vp, vp, vp, vp, vp, C.POINTER(vp),
+                                   C.POINTER(Options), C.POINTER(Inform)]
+    L.spldlt_solve.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(Options),
+                               C.POINTER(Inform)]
+    L.spldlt_free_akeep.argtypes = [C.POINTER(vp)]
+    L.spldlt_free_fkeep.argtypes = [C.POINTER(vp)]
+    L.spldlt_create_symbolic_tree.restype = vp
+    L.spldlt_create_symbolic_tree.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                              C.c_int, vp, vp, vp, vp]
+    L.spldlt_destroy_symbolic_tree.argtypes = [vp]
+    L.spldlt_create_numeric_tree_dbl.restype = vp
+    L.spldlt_create_numeric_tree_dbl.argtypes = [C.c_bool, vp, vp, vp, vp, vp,
+                                                 C.POINTER(OptionsC), C.POINTER(InformC)]
+    L.spldlt_create_numeric_tree_posdef_dbl.restype = vp
+    L.spldlt_create_numeric_tree_posdef_dbl.argtypes = [vp, vp, vp, vp, vp, C.POINTER(OptionsC),
+                                                        C.POINTER(InformC)]
+    L.spldlt_destroy_numeric_tree_dbl.argtypes = [C.c_bool, vp]
+    L.spldlt_destroy_numeric_tree_posdef_dbl.argtypes = [vp]
+    for name in ("fwd", "bwd", "diag", "diag_bwd"):
+        f = getattr(L, f"spldlt_tree_solve_{name}_dbl")
+        f.argtypes = [C.c_bool, vp, C.c_int, vp, C.c_int]
+        f.restype = C.c_int
+    for name in ("fwd", "bwd"):
+        f = getattr(L, f"spldlt_tree_solve_{name}_posdef_dbl")
+        f.argtypes = [vp, C.c_int, vp, C.c_int]
+        f.restype = C.c_int
+    L.sylver_b200_version.restype = C.c_char_p
+    L.sylver_b200_akeep_view.argtypes = [vp, C.POINTER(SymbolicView)]
+    L.sylver_b200_akeep_tree.restype = vp
+    L.sylver_b200_akeep_tree.argtypes = [vp]
+    L.sylver_b200_symbolic_tree_cmap.argtypes = [vp, C.POINTER(lp), C.POINTER(ip)]
+    L.sylver_b200_fkeep_tree.restype = vp
+    L.sylver_b200_fkeep_tree.argtypes = [vp]
+    L.sylver_b200_numeric_tree_timings.argtypes = [vp, dp]
+    L.sylver_b200_numeric_tree_get_front.argtypes = [vp, C.c_int, ip, ip, vp, vp]
+    L.sylver_b200_factor_front_posdef.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
+                                                  C.POINTER(C.c_float)]
+    L.sylver_b200_bench_dmma.restype = C.c_double
+    L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sylver_b200_bench_copy.restype = C.c_double
+    L.sylver_b200_bench_copy.argtypes = [C.c_long, C.c_int]
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return int(lib().sylver_b200_device_count())
+
+
+def require_gpu() -> None:
+    if device_count() == 0:
+        raise RuntimeError("sylver_b200: no CUDA device visible; the factorization path has no CPU fallback")
+
+
+def default_options() -> Options:
+    o = Options()
+    lib().sylver_default_options(C.byref(o))
+    o.ordering = 0     # the order is always an input here (METIS is not part of this path)
+    return o
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)       # raw (device) address
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Solver:
+    """Mirror of the reference C example's call sequence
+    (/root/reference/examples/C/spldlt_simple_example_c.c:27-75)."""
+
+    def __init__(self, ngpu: int = 1):
+        self.L = lib()
+        self.L.sylver_init(1, ngpu)
+        self.akeep = C.c_void_p(None)
+        self.fkeep = C.c_void_p(None)
+        self.options = default_options()
+        self.inform = Inform()
+        self.n = 0
+
+    def analyse(self, n, ptr, row, order, val=None, check=False):
+        self.n = n
+        self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        self.row = np.ascontiguousarray(row, dtype=np.int32)
+        self.order = np.ascontiguousarray(order, dtype=np.int32).copy()
+        self.L.spldlt_analyse(n, _ptr(self.order), _ptr(self.ptr), _ptr(self.row), _ptr(val),
+                              C.byref(self.akeep), check, C.byref(self.options), C.byref(self.inform))
+        return self.inform
+
+    def symbolic(self):
+        """Return the seam arrays as numpy copies (1-based values, as in Fortran)."""
+        v = SymbolicView()
+        if self.L.sylver_b200_akeep_view(self.akeep, C.byref(v)) != 0:
+            raise RuntimeError("analyse has not been run")
+        nn = v.nnodes
+        out = dict(n=v.n, nnodes=nn, num_factor=v.num_factor, num_flops=v.num_flops)
+        out["sptr"] = np.ctypeslib.as_array(v.sptr, (nn + 1,)).copy()
+        out["sparent"] = np.ctypeslib.as_array(v.sparent, (max(nn, 1),)).copy()[:nn]
+        out["rptr"] = np.ctypeslib.as_array(v.rptr, (nn + 1,)).copy()
+        nr = int(out["rptr"][nn] - 1) if nn else 0
+        out["rlist"] = np.ctypeslib.as_array(v.rlist, (max(nr, 1),)).copy()[:nr]
+        out["nptr"] = np.ctypeslib.as_array(v.nptr, (nn + 1,)).copy()
+        ne = int(out["nptr"][nn] - 1) if nn else 0
+        out["nlist"] = np.ctypeslib.as_array(v.nlist, (max(2 * ne, 1),)).copy()[:2 * ne]
+        out["order"] = np.ctypeslib.as_array(v.order, (max(v.n, 1),)).copy()[:v.n]
+        out["invp"] = np.ctypeslib.as_array(v.invp, (max(v.n, 1),)).copy()[:v.n]
+        return out
+
+    def cmap(self):
+        tree = self.L.sylver_b200_akeep_tree(self.akeep)
+        cptr = C.POINTER(C.c_long)()
+        cm = C.POINTER(C.c_int)()
+        self.L.sylver_b200_symbolic_tree_cmap(tree, C.byref(cptr), C.byref(cm))
+        nn = self.symbolic()["nnodes"]
+        p = np.ctypeslib.as_array(cptr, (nn + 1,)).copy()
+        return p, np.ctypeslib.as_array(cm, (max(int(p[nn]), 1),)).copy()[:int(p[nn])]
+
+    def factorize(self, val, posdef: bool, scale=None):
+        """val: numpy array (host) or an int device address."""
+        if not isinstance(val, int):
+            val = np.ascontiguousarray(val, dtype=np.float64)
+        self._val = val
+        self.L.spldlt_factorize(posdef, _ptr(self.ptr), _ptr(self.row), _ptr(val), _ptr(scale),
+                                self.akeep, C.byref(self.fkeep), C.byref(self.options),
+                                C.byref(self.inform))
+        return self.inform
+
+    def timings(self):
+        out = (C.c_double * 4)()
+        tree = self.L.sylver_b200_fkeep_tree(self.fkeep)
+        if not tree or self.L.sylver_b200_numeric_tree_timings(tree, out) != 0:
+            return None
+        return dict(device_s=out[0], h2d_s=out[1], wall_s=out[2], launches=int(out[3]))
+
+    def solve(self, b, job: int = 0):
+        x = np.array(b, dtype=np.float64, order="F", copy=True)
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        self.L.spldlt_solve(job, nrhs, _ptr(x), self.n, self.akeep, self.fkeep,
+                            C.byref(self.options), C.byref(self.inform))
+        return x
+
+    def free(self):
+        self.L.spldlt_free_fkeep(C.byref(self.fkeep))
+        self.L.spldlt_free_akeep(C.byref(self.akeep))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,375 @@
+// C ABI of libsylver_b200.so: the public SyLVER API and the Fortran->C++ seam,
+// re-stated in C++ (the reference implements them in Fortran:
+// src/interfaces/C/sylver_ciface.F90:304-826, src/spldlt_analyse_mod.F90:587-890,
+// src/spldlt_factorize_mod.F90:473-898,901-1060).  See include/sylver_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/sylver_b200.h"
+#include "analyse.hpp"
+#include "engine.hpp"
+
+using namespace sylver_b200;
+
+namespace sylver_b200 {
+void symbolic_tree_forget(const SymbolicTree* st);
+}
+
+namespace {
+
+struct AKeep {
+   Symbolic sym;
+   SymbolicTree* tree = nullptr;
+   sylver_inform_t inform{};
+   bool analysed = false;
+};
+
+struct FKeep {
+   NumericTree* tree = nullptr;
+   AKeep* akeep = nullptr;
+   bool posdef = false;
+   std::vector<double> scaling;   // in elimination order (empty if none)
+   sylver_inform_t inform{};
+};
+
+int g_ngpu = 1;
+
+sylver_inform_t inform_default() {
+   sylver_inform_t inf;
+   std::memset(&inf, 0, sizeof(inf));
+   return inf;
+}
+
+// src/sylver_ciface_mod.F90:37-55 (copy_options_f2c)
+sylver_options_c options_to_c(const sylver_options_t* o) {
+   sylver_options_c c{};
+   c.print_level = o->print_level;
+   c.action = o->action;
+   c.small = o->small;
+   c.u = o->u;
+   c.multiplier = 1.1;   // undocumented Fortran-side default, not in the C struct
+   c.small_subtree_threshold = o->small_subtree_threshold;
+   c.nb = o->nb;
+   c.pivot_method = o->pivot_method;
+   c.failed_pivot_method = o->failed_pivot_method;
+   c.cpu_topology = o->cpu_topology;
+   return c;
+}
+
+// src/sylver_ciface_mod.F90:59-78 (copy_inform_c2f) + flag merge of
+// src/sylver_ciface.cxx:52-64.
+void fold_stats(const sylver_inform_c& s, sylver_inform_t* inf) {
+   if (s.flag < 0)
+      inf->flag = std::min(inf->flag, s.flag);
+   else if (inf->flag >= 0)
+      inf->flag = std::max(inf->flag, s.flag);
+   inf->num_delay = s.num_delay;
+   inf->num_neg = s.num_neg;
+   inf->num_two = s.num_two;
+   inf->matrix_rank = inf->matrix_rank - s.num_zero;
+   inf->maxfront = std::max(inf->maxfront, s.maxfront);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sylver_b200_version(void) { return "sylver_b200 0.1 (sm_100a)"; }
+int sylver_b200_device_count(void) { return device_count(); }
+
+void sylver_init(int ncpu, int ngpu) {
+   (void)ncpu;
+   g_ngpu = std::max(1, ngpu);
+}
+void sylver_finalize(void) {}
+
+void sylver_default_options(sylver_options_t* o) {
+   // src/sylver_datatypes_mod.F90:97-198 via src/interfaces/C/sylver_ciface.F90:304-370
+   std::memset(o, 0, sizeof(*o));
+   o->array_base = 0;
+   o->print_level = 0;
+   o->unit_diagnostics = 6;
+   o->unit_error = 6;
+   o->unit_warning = 6;
+   o->ordering = 1;
+   o->nemin = 32;
+   o->prune_tree = true;
+   o->min_gpu_work = 5000000000L;
+   o->scaling = 0;
+   o->pivot_method = 2;
+   o->small = 1e-20;
+   o->u = 0.01;
+   o->small_subtree_threshold = 4000000L;
+   o->nb = 256;
+   o->cpu_topology = 1;
+   o->action = true;
+   o->use_gpu = true;
+   o->gpu_perf_coeff = 1.0;
+   o->failed_pivot_method = 1;
+   o->scheduler = 1;
+}
+
+void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double const* val, void** akeep_p,
+                    bool check, sylver_options_t const* options, sylver_inform_t* inform) {
+   (void)val;
+   (void)check;   // matrix cleaning (check=true) is a pre-processing step outside this path
+   *inform = inform_default();
+   AKeep* ak = static_cast<AKeep*>(*akeep_p);
+   if (!ak) {
+      ak = new (std::nothrow) AKeep();
+      if (!ak) { inform->flag = SYLVER_ERROR_ALLOCATION; return; }
+      *akeep_p = ak;
+   } else {
+      if (ak->tree) { symbolic_tree_forget(ak->tree); delete ak->tree; ak->tree = nullptr; }
+      ak->sym = Symbolic();
+      ak->analysed = false;
+   }
+   if (n < 0) { inform->flag = SYLVER_ERROR_A_N_OOR; ak->inform = *inform; return; }
+   if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; ak->inform = *inform; return; }
+   if (options->ordering < 0 || options->ordering > 2) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
+   if (options->ordering != 0) {
+      // METIS / matching orderings are un-vendored pre-processing: order is an input here
+      inform->flag = (options->ordering == 2 && !val) ? SYLVER_ERROR_VAL : SYLVER_ERROR_UNIMPLEMENTED;
+      ak->inform = *inform;
+      return;
+   }
+   if (n > 0 && !order) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
+   int flag;
+   try {
+      flag = analyse(n, ptr, row, order, options->nemin, ak->sym);
+   } catch (std::bad_alloc&) {
+      flag = ANAL_ERROR_ALLOCATION;
+   }
+   if (flag < 0) { inform->flag = flag; ak->inform = *inform; return; }
+   inform->flag = flag;
+   Symbolic& s = ak->sym;
+   if (n > 0) {
+      int tflag = 0;
+      ak->tree = symbolic_tree_create(n, s.nnodes, s.sptr.data(), s.sparent.data(), s.rptr.data(), s.rlist.data(),
+                                      s.nptr.data(), s.nlist.data(), &tflag);
+      if (!ak->tree) { inform->flag = tflag ? tflag : SYLVER_ERROR_UNKNOWN; ak->inform = *inform; return; }
+      for (int i = 0; i < n; ++i) order[i] = std::abs(s.order[i]);
+   }
+   inform->num_factor = s.num_factor;
+   inform->num_flops = s.num_flops;
+   inform->maxfront = s.maxfront;
+   inform->maxdepth = s.maxdepth;
+   inform->matrix_rank = s.matrix_rank;
+   inform->num_sup = s.nnodes;
+   ak->analysed = true;
+   ak->inform = *inform;
+}
+
+void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const* val, double* scale,
+                      void* akeep_v, void** fkeep_p, sylver_options_t const* options, sylver_inform_t* inform) {
+   (void)ptr;
+   (void)row;
+   AKeep* ak = static_cast<AKeep*>(akeep_v);
+   if (!ak || !ak->analysed || ak->inform.flag < 0) {
+      *inform = inform_default();
+      inform->flag = SYLVER_ERROR_CALL_SEQUENCE;
+      return;
+   }
+   *inform = ak->inform;
+   FKeep* fk = static_cast<FKeep*>(*fkeep_p);
+   if (!fk) {
+      fk = new (std::nothrow) FKeep();
+      if (!fk) { inform->flag = SYLVER_ERROR_ALLOCATION; return; }
+      *fkeep_p = fk;
+   }
+   const int n = ak->sym.n;
+   if (!options->action && n != ak->inform.matrix_rank) { inform->flag = SYLVER_ERROR_SINGULAR; fk->inform = *inform; return; }
+   if (ak->sym.nnodes == 0) { inform->flag = SYLVER_SUCCESS; inform->matrix_rank = 0; fk->inform = *inform; return; }
+   if (!val) { inform->flag = SYLVER_ERROR_VAL; fk->inform = *inform; return; }
+   if (options->scaling > 0) {
+      // MC64 / auction / MC77 scalings are pre-processing outside this path
+      inform->flag = SYLVER_ERROR_UNIMPLEMENTED;
+      fk->inform = *inform;
+      return;
+   }
+   // user supplied scaling, permuted to elimination order (spldlt_factorize_mod.F90:744-749)
+   fk->scaling.clear();
+   if (scale) {
+      fk->scaling.resize(n);
+      for (int i = 0; i < n; ++i) fk->scaling[i] = scale[ak->sym.invp[i] - 1];
+   }
+   sylver_options_c copt = options_to_c(options);
+   sylver_inform_c stats{};
+   const double* sc = fk->scaling.empty() ? nullptr : fk->scaling.data();
+   if (fk->tree && fk->akeep == ak && fk->posdef == posdef && posdef) {
+      numeric_tree_refactor(fk->tree, val, sc, &stats);
+   } else {
+      if (fk->tree) { numeric_tree_destroy(fk->tree); fk->tree = nullptr; }
+      fk->tree = numeric_tree_create(posdef, ak->tree, val, sc, &copt, &stats);
+   }
+   fk->akeep = ak;
+   fk->posdef = posdef;
+   fold_stats(stats, inform);
+   if (inform->flag >= 0 && n != inform->matrix_rank)
+      inform->flag = options->action ? SYLVER_WARNING_FACT_SINGULAR : SYLVER_ERROR_SINGULAR;
+   fk->inform = *inform;
+}
+
+void spldlt_solve(int job, int nrhs, double* x, int ldx, void* akeep_v, void* fkeep_v,
+                  sylver_options_t const* options, sylver_inform_t* inform) {
+   (void)options;
+   AKeep* ak = static_cast<AKeep*>(akeep_v);
+   FKeep* fk = static_cast<FKeep*>(fkeep_v);
+   if (!ak || !fk || !ak->analysed) {
+      *inform = inform_default();
+      inform->flag = SYLVER_ERROR_CALL_SEQUENCE;
+      return;
+   }
+   *inform = fk->inform;
+   if (fk->inform.flag < 0) { inform->flag = SYLVER_ERROR_CALL_SEQUENCE; return; }
+   const int n = ak->sym.n;
+   if (n == 0 || ak->sym.nnodes == 0) return;
+   if (!fk->tree) { inform->flag = SYLVER_ERROR_CALL_SEQUENCE; return; }
+   if (ldx < n || nrhs < 1) { inform->flag = SYLVER_ERROR_X_SIZE; return; }
+   if (job < 0 || job > 4) { inform->flag = SYLVER_ERROR_JOB_OOR; return; }
+   if (fk->posdef && (job == 2 || job == 4)) { inform->flag = SYLVER_ERROR_JOB_OOR; return; }
+   const std::vector<int>& invp = ak->sym.invp;
+   const bool sc = !fk->scaling.empty();
+   std::vector<double> x2((size_t)n * nrhs);
+   for (int r = 0; r < nrhs; ++r)
+      for (int i = 0; i < n; ++i) {
+         double v = x[(size_t)r * ldx + invp[i] - 1];
+         if (sc && (job == 0 || job == 1)) v *= fk->scaling[i];
+         x2[(size_t)r * n + i] = v;
+      }
+   int flag = numeric_tree_solve(fk->tree, job, nrhs, x2.data(), n);
+   if (flag < 0) { inform->flag = flag; return; }
+   for (int r = 0; r < nrhs; ++r)
+      for (int i = 0; i < n; ++i) {
+         double v = x2[(size_t)r * n + i];
+         if (sc && (job == 0 || job == 3 || job == 4)) v *= fk->scaling[i];
+         x[(size_t)r * ldx + invp[i] - 1] = v;
+      }
+}
+
+void spldlt_free_akeep(void** akeep_p) {
+   if (!akeep_p || !*akeep_p) return;
+   AKeep* ak = static_cast<AKeep*>(*akeep_p);
+   if (ak->tree) { symbolic_tree_forget(ak->tree); delete ak->tree; }
+   delete ak;
+   *akeep_p = nullptr;
+}
+
+void spldlt_free_fkeep(void** fkeep_p) {
+   if (!fkeep_p || !*fkeep_p) return;
+   FKeep* fk = static_cast<FKeep*>(*fkeep_p);
+   if (fk->tree) numeric_tree_destroy(fk->tree);
+   delete fk;
+   *fkeep_p = nullptr;
+}
+
+// ------------------------------- seam ------------------------------------
+
+void* spldlt_create_symbolic_tree(void* akeep, int n, int nnodes, int const* sptr, int const* sparent,
+                                  long const* rptr, int const* rlist, long const* nptr, long const* nlist,
+                                  int nsubtrees, int const* subtrees, int const* small, int const* contrib_dest,
+                                  int const* exec_loc) {
+   (void)akeep; (void)subtrees; (void)small; (void)contrib_dest; (void)exec_loc;
+   if (nsubtrees != 0) {
+      fprintf(stderr, "sylver_b200: pruned subtrees are not delegated (nsubtrees must be 0; every front runs on the GPU)\n");
+      return nullptr;
+   }
+   int flag = 0;
+   try {
+      return symbolic_tree_create(n, nnodes, sptr, sparent, rptr, rlist, nptr, nlist, &flag);
+   } catch (std::bad_alloc&) {
+      return nullptr;
+   }
+}
+void spldlt_destroy_symbolic_tree(void* t) {
+   SymbolicTree* st = static_cast<SymbolicTree*>(t);
+   if (!st) return;
+   symbolic_tree_forget(st);
+   delete st;
+}
+
+void* spldlt_create_numeric_tree_dbl(bool posdef, void* fkeep, void* symbolic_tree, double* aval,
+                                     const double* scaling, void** child_contrib, sylver_options_c* options,
+                                     sylver_inform_c* stats) {
+   (void)fkeep; (void)child_contrib;
+   return numeric_tree_create(posdef, static_cast<SymbolicTree*>(symbolic_tree), aval, scaling, options, stats);
+}
+void* spldlt_create_numeric_tree_posdef_dbl(void* fkeep, void* symbolic_tree, double* aval, const double* scaling,
+                                            void** child_contrib, sylver_options_c* options,
+                                            sylver_inform_c* stats) {
+   return spldlt_create_numeric_tree_dbl(true, fkeep, symbolic_tree, aval, scaling, child_contrib, options, stats);
+}
+void spldlt_destroy_numeric_tree_dbl(bool posdef, void* tree) {
+   (void)posdef;
+   numeric_tree_destroy(static_cast<NumericTree*>(tree));
+}
+void spldlt_destroy_numeric_tree_posdef_dbl(void* tree) { numeric_tree_destroy(static_cast<NumericTree*>(tree)); }
+
+int spldlt_tree_solve_fwd_dbl(bool, void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 1, nrhs, x, ldx);
+}
+int spldlt_tree_solve_bwd_dbl(bool, void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 3, nrhs, x, ldx);
+}
+int spldlt_tree_solve_diag_dbl(bool, void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 2, nrhs, x, ldx);
+}
+int spldlt_tree_solve_diag_bwd_dbl(bool, void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 4, nrhs, x, ldx);
+}
+int spldlt_tree_solve_fwd_posdef_dbl(void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 1, nrhs, x, ldx);
+}
+int spldlt_tree_solve_bwd_posdef_dbl(void const* t, int nrhs, double* x, int ldx) {
+   return numeric_tree_solve(static_cast<const NumericTree*>(t), 3, nrhs, x, ldx);
+}
+
+// ------------------------------ helpers ----------------------------------
+
+int sylver_b200_akeep_view(void* akeep, sylver_b200_symbolic_view* v) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   if (!ak || !ak->analysed) return -1;
+   const Symbolic& s = ak->sym;
+   v->n = s.n; v->nnodes = s.nnodes;
+   v->sptr = s.sptr.data(); v->sparent = s.sparent.data(); v->rptr = s.rptr.data();
+   v->rlist = s.rlist.data(); v->nptr = s.nptr.data(); v->nlist = s.nlist.data();
+   v->order = s.order.data(); v->invp = s.invp.data();
+   v->num_factor = s.num_factor; v->num_flops = s.num_flops;
+   return 0;
+}
+
+void* sylver_b200_akeep_tree(void* akeep) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   return ak ? ak->tree : nullptr;
+}
+
+int sylver_b200_symbolic_tree_cmap(void* symbolic_tree, long const** cptr, int const** cmap) {
+   SymbolicTree* st = static_cast<SymbolicTree*>(symbolic_tree);
+   if (!st) return -1;
+   *cptr = st->cmapoff.data();
+   *cmap = st->cmap.data();
+   return 0;
+}
+
+void* sylver_b200_fkeep_tree(void* fkeep) {
+   FKeep* fk = static_cast<FKeep*>(fkeep);
+   return fk ? fk->tree : nullptr;
+}
+
+int sylver_b200_numeric_tree_timings(void const* tree, double* out4) {
+   if (!tree) return -1;
+   numeric_tree_timings(static_cast<const NumericTree*>(tree), out4);
+   return 0;
+}
+
+int sylver_b200_numeric_tree_get_front(void const* tree, int node, int* m, int* n, double* l, double* contrib) {
+   if (!tree) return -1;
+   return numeric_tree_get_front(static_cast<const NumericTree*>(tree), node, m, n, l, contrib);
+}
+
+}  // extern "C"

@@ -1,0 +1,702 @@
+// B200 numeric factorization engine: plan construction, device arenas, the
+// level-batched CUDA stream/graph scheduler and the triangular solves.
+//
+// Scheduling model (replaces StarPU task submission, reference
+// src/NumericTree.hxx:186-406 / src/NumericTreePosdef.hxx:133-353):
+//   fronts are grouped by height in the assembly tree; every kernel launch is
+//   *batched* over all fronts of a level (tree parallelism inside a launch),
+//   block columns of the same index advance together (node parallelism inside
+//   a launch), and for positive definite problems the whole launch sequence is
+//   captured once into a CUDA graph and replayed per factorization.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "kernels.cuh"
+#include "kernels_solve.cuh"
+
+namespace sylver_b200 {
+
+#define CU_TRY(expr)                                                                    \
+   do {                                                                                 \
+      cudaError_t e__ = (expr);                                                         \
+      if (e__ != cudaSuccess) {                                                         \
+         fprintf(stderr, "sylver_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName(e__), \
+                 __FILE__, __LINE__, #expr);                                            \
+         throw CudaFailure{(int)e__};                                                   \
+      }                                                                                 \
+   } while (0)
+
+struct CudaFailure {
+   int code;
+};
+
+int device_count() {
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+   }
+   return n;
+}
+
+template <typename T>
+static T* dev_upload(const T* h, size_t count) {
+   T* d = nullptr;
+   CU_TRY(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+   if (count) CU_TRY(cudaMemcpy(d, h, count * sizeof(T), cudaMemcpyHostToDevice));
+   return d;
+}
+template <typename T>
+static T* dev_upload(const std::vector<T>& v) {
+   return dev_upload(v.data(), v.size());
+}
+
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// ===========================================================================
+// SymbolicTree
+// ===========================================================================
+SymbolicTree::~SymbolicTree() {
+   if (!on_device) return;
+   cudaFree(d_rlist); cudaFree(d_rptr); cudaFree(d_nlist); cudaFree(d_anode); cudaFree(d_nrow);
+   cudaFree(d_ncol); cudaFree(d_parent); cudaFree(d_nchild); cudaFree(d_cmap); cudaFree(d_cmapoff);
+   cudaFree(d_level_nodes);
+}
+
+// Host-only copies needed again at upload time
+struct SymbolicExtra {
+   std::vector<long> rptr1;   // 1-based rptr as given
+   std::vector<long> nlist;   // (src,dest) pairs as given
+   std::vector<int> anode;    // owning front of each entry
+};
+static std::map<const SymbolicTree*, SymbolicExtra>& extras() {
+   static std::map<const SymbolicTree*, SymbolicExtra> m;
+   return m;
+}
+
+SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int* sparent,
+                                   const long* rptr, const int* rlist, const long* nptr,
+                                   const long* nlist, int* flag) {
+   *flag = 0;
+   SymbolicTree* st = new SymbolicTree();
+   st->n = n;
+   st->nnodes = nnodes;
+   st->nrow.resize(nnodes); st->ncol.resize(nnodes); st->parent.resize(nnodes);
+   st->nchild.assign(nnodes + 1, 0); st->level.assign(nnodes + 1, 0);
+   st->rptr.resize(nnodes + 1);
+   for (int i = 0; i <= nnodes; ++i) st->rptr[i] = rptr[i] - 1;
+   st->rlist.assign(rlist, rlist + st->rptr[nnodes]);
+   long flops = 0;
+   for (int i = 0; i < nnodes; ++i) {
+      st->nrow[i] = (int)(rptr[i + 1] - rptr[i]);
+      st->ncol[i] = sptr[i + 1] - sptr[i];
+      st->parent[i] = std::min(sparent[i] - 1, nnodes);
+      if (st->parent[i] <= i) { *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr; }
+      st->nchild[st->parent[i]]++;
+      long mm = st->nrow[i] - st->ncol[i];
+      for (long j = 1; j <= st->ncol[i]; ++j) flops += (mm + j) * (mm + j);
+   }
+   st->num_flops = flops;
+   // children lists, decreasing node index (reference src/SymbolicTree.cxx:51-55)
+   st->child_ptr.assign(nnodes + 2, 0);
+   for (int i = 0; i <= nnodes; ++i) st->child_ptr[i + 1] = st->child_ptr[i] + st->nchild[i];
+   st->child_list.resize(st->child_ptr[nnodes + 1]);
+   {
+      std::vector<int> fill(st->child_ptr.begin(), st->child_ptr.end() - 1);
+      for (int i = nnodes - 1; i >= 0; --i) st->child_list[fill[st->parent[i]]++] = i;
+   }
+   // per-edge assembly maps (two-pointer merge of sorted row lists)
+   st->cmapoff.assign(nnodes + 1, 0);
+   for (int i = 0; i < nnodes; ++i) st->cmapoff[i + 1] = st->cmapoff[i] + (st->nrow[i] - st->ncol[i]);
+   st->cmap.resize(st->cmapoff[nnodes]);
+   for (int c = 0; c < nnodes; ++c) {
+      const int p = st->parent[c];
+      const int k = st->nrow[c] - st->ncol[c];
+      if (k == 0) continue;
+      if (p >= nnodes) {   // root with a contribution: only legal for stand-alone dense fronts
+         for (int i = 0; i < k; ++i) st->cmap[st->cmapoff[c] + i] = -1;
+         continue;
+      }
+      const int* cr = &st->rlist[st->rptr[c] + st->ncol[c]];
+      const int* pr = &st->rlist[st->rptr[p]];
+      const int pm = st->nrow[p];
+      int q = 0;
+      for (int i = 0; i < k; ++i) {
+         while (q < pm && pr[q] < cr[i]) ++q;
+         if (q >= pm || pr[q] != cr[i]) { *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr; }
+         st->cmap[st->cmapoff[c] + i] = q;
+      }
+   }
+   // levels = height above the leaves
+   for (int i = 0; i < nnodes; ++i) {
+      const int p = st->parent[i];
+      st->level[p] = std::max(st->level[p], st->level[i] + 1);
+   }
+   int nlev = 0;
+   for (int i = 0; i < nnodes; ++i) nlev = std::max(nlev, st->level[i] + 1);
+   st->nlevels = nlev;
+   st->level_ptr.assign(nlev + 1, 0);
+   for (int i = 0; i < nnodes; ++i) st->level_ptr[st->level[i] + 1]++;
+   for (int l = 0; l < nlev; ++l) st->level_ptr[l + 1] += st->level_ptr[l];
+   st->level_nodes.resize(nnodes);
+   {
+      std::vector<int> fill(st->level_ptr.begin(), st->level_ptr.end() - 1);
+      for (int i = 0; i < nnodes; ++i) st->level_nodes[fill[st->level[i]]++] = i;
+      for (int l = 0; l < nlev; ++l)
+         std::stable_sort(st->level_nodes.begin() + st->level_ptr[l], st->level_nodes.begin() + st->level_ptr[l + 1],
+                          [&](int a, int b) { return st->ncol[a] > st->ncol[b]; });
+   }
+   // A -> front map
+   SymbolicExtra& ex = extras()[st];
+   ex.rptr1.assign(rptr, rptr + nnodes + 1);
+   st->nent = nnodes ? nptr[nnodes] - 1 : 0;
+   ex.nlist.assign(nlist, nlist + 2 * st->nent);
+   ex.anode.resize(st->nent);
+   for (int i = 0; i < nnodes; ++i)
+      for (long e = nptr[i] - 1; e < nptr[i + 1] - 1; ++e) ex.anode[e] = i;
+   st->nval = 0;
+   for (long e = 0; e < st->nent; ++e) st->nval = std::max(st->nval, nlist[2 * e]);
+   return st;
+}
+
+static void symbolic_tree_upload(SymbolicTree* st) {
+   if (st->on_device) return;
+   SymbolicExtra& ex = extras()[st];
+   CU_TRY(cudaGetDevice(&st->device));
+   st->d_rlist = dev_upload(st->rlist);
+   st->d_rptr = dev_upload(ex.rptr1);
+   st->d_nlist = dev_upload(ex.nlist);
+   st->d_anode = dev_upload(ex.anode);
+   st->d_nrow = dev_upload(st->nrow);
+   st->d_ncol = dev_upload(st->ncol);
+   st->d_parent = dev_upload(st->parent);
+   st->d_nchild = dev_upload(st->nchild);
+   st->d_cmap = dev_upload(st->cmap);
+   st->d_cmapoff = dev_upload(st->cmapoff);
+   st->d_level_nodes = dev_upload(st->level_nodes);
+   st->on_device = true;
+   ex.nlist.clear(); ex.nlist.shrink_to_fit();
+   ex.anode.clear(); ex.anode.shrink_to_fit();
+}
+
+void symbolic_tree_forget(const SymbolicTree* st) { extras().erase(st); }
+
+// ===========================================================================
+// Contribution arena planning (static: m - n never changes, even with delays)
+// ===========================================================================
+namespace {
+struct SegAlloc {
+   // first-fit free list over [0, inf), sizes in doubles
+   std::map<long, long> free_;   // offset -> size
+   long top = 0;
+   long peak = 0;
+   long alloc(long sz) {
+      for (auto it = free_.begin(); it != free_.end(); ++it) {
+         if (it->second >= sz) {
+            long off = it->first;
+            long rem = it->second - sz;
+            free_.erase(it);
+            if (rem > 0) free_[off + sz] = rem;
+            return off;
+         }
+      }
+      // extend the top (merge with a trailing free segment if adjacent)
+      long off = top;
+      if (!free_.empty()) {
+         auto last = std::prev(free_.end());
+         if (last->first + last->second == top) {
+            off = last->first;
+            free_.erase(last);
+         }
+      }
+      top = off + sz;
+      peak = std::max(peak, top);
+      return off;
+   }
+   void release(long off, long sz) {
+      auto it = free_.emplace(off, sz).first;
+      auto nx = std::next(it);
+      if (nx != free_.end() && it->first + it->second == nx->first) {
+         it->second += nx->second;
+         free_.erase(nx);
+      }
+      if (it != free_.begin()) {
+         auto pv = std::prev(it);
+         if (pv->first + pv->second == it->first) {
+            pv->second += it->second;
+            free_.erase(it);
+         }
+      }
+   }
+};
+}  // namespace
+
+// ===========================================================================
+// NumericTree
+// ===========================================================================
+struct LevelStep {
+   int cnt;             // fronts of the level that own block column `s`
+   int wld;             // stride of the inverse slots for this step
+   int trsm_tiles, upd_tiles;
+   size_t trsm_prefix, upd_prefix;   // offsets into d_prefix
+};
+struct LevelPlan {
+   int first, count;               // range in level_nodes
+   int max_children;
+   std::vector<std::pair<size_t, int>> asm_work;   // per child ordinal: (offset, count) in d_asm_work
+   std::vector<LevelStep> steps;
+   int contrib_tiles;
+   size_t contrib_prefix;
+};
+
+struct NumericTree {
+   SymbolicTree* st = nullptr;
+   bool posdef = true;
+   sylver_options_c opt{};
+   int nb = 128;
+   // per-front geometry (host) + device mirrors
+   std::vector<int> m, n, ldl, ldc;
+   std::vector<long> loff, coff;
+   int *d_m = nullptr, *d_n = nullptr, *d_ldl = nullptr, *d_ldc = nullptr;
+   long *d_loff = nullptr, *d_coff = nullptr;
+   double* d_L = nullptr; size_t L_doubles = 0;
+   double* d_C = nullptr; size_t C_doubles = 0;
+   double* d_W = nullptr; size_t W_doubles = 0;
+   double* d_aval = nullptr; size_t aval_count = 0;
+   double* d_scaling = nullptr;
+   int* d_fail = nullptr;
+   int* d_prefix = nullptr;
+   int2* d_asm_work = nullptr;
+   std::vector<LevelPlan> levels;
+   DevTree T{};
+   cudaStream_t stream = nullptr;
+   cudaGraphExec_t graph = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   long launches = 0;
+   double t_device = 0, t_h2d = 0, t_wall = 0;
+   // solve workspace
+   double* d_xw = nullptr;        // sum of m doubles
+   long* d_xwoff = nullptr;
+   std::vector<long> xwoff;
+   int* d_child_ptr = nullptr; int* d_child_list = nullptr;
+};
+
+bool numeric_tree_posdef(const NumericTree* nt) { return nt->posdef; }
+
+static void build_posdef_plan(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes;
+   const int nb = nt->nb;
+   nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N); nt->ldc.resize(N);
+   nt->loff.resize(N); nt->coff.assign(N, 0);
+   long loff = 0;
+   for (int f = 0; f < N; ++f) {
+      nt->m[f] = st->nrow[f];
+      nt->n[f] = st->ncol[f];
+      nt->ldl[f] = round_up(nt->m[f], 4);
+      nt->ldc[f] = round_up(std::max(nt->m[f] - nt->n[f], 1), 4);
+      nt->loff[f] = loff;
+      loff += (long)nt->ldl[f] * nt->n[f];
+   }
+   nt->L_doubles = loff + 4;
+   // contribution arena: allocate a level's blocks, then release its children's
+   SegAlloc sa;
+   for (int l = 0; l < st->nlevels; ++l) {
+      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
+         const int f = st->level_nodes[i];
+         const long k = nt->m[f] - nt->n[f];
+         if (k > 0) nt->coff[f] = sa.alloc((long)nt->ldc[f] * k);
+      }
+      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
+         const int f = st->level_nodes[i];
+         for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
+            const int c = st->child_list[ci];
+            const long k = nt->m[c] - nt->n[c];
+            if (k > 0) sa.release(nt->coff[c], (long)nt->ldc[c] * k);
+         }
+      }
+   }
+   nt->C_doubles = sa.peak + 4;
+
+   // work lists
+   std::vector<int> prefix;
+   std::vector<int2> asmw;
+   size_t wmax = 1;
+   nt->levels.resize(st->nlevels);
+   for (int l = 0; l < st->nlevels; ++l) {
+      LevelPlan& lp = nt->levels[l];
+      lp.first = st->level_ptr[l];
+      lp.count = st->level_ptr[l + 1] - lp.first;
+      const int* fr = &st->level_nodes[lp.first];
+      lp.max_children = 0;
+      int maxn = 0;
+      for (int i = 0; i < lp.count; ++i) {
+         lp.max_children = std::max(lp.max_children, st->nchild[fr[i]]);
+         maxn = std::max(maxn, nt->n[fr[i]]);
+      }
+      // assembly: q-th child of every parent of this level
+      for (int q = 0; q < lp.max_children; ++q) {
+         size_t off = asmw.size();
+         for (int i = 0; i < lp.count; ++i) {
+            const int f = fr[i];
+            if (st->nchild[f] <= q) continue;
+            const int c = st->child_list[st->child_ptr[f] + q];
+            const int k = nt->m[c] - nt->n[c];
+            for (int j0 = 0; j0 < k; j0 += 32) asmw.push_back(make_int2(c, j0));
+         }
+         lp.asm_work.emplace_back(off, (int)(asmw.size() - off));
+      }
+      // block-column steps
+      const int nsteps = (maxn + nb - 1) / nb;
+      lp.steps.resize(nsteps);
+      for (int s = 0; s < nsteps; ++s) {
+         LevelStep& ls = lp.steps[s];
+         const int p0 = s * nb;
+         int cnt = 0;
+         while (cnt < lp.count && nt->n[fr[cnt]] > p0) ++cnt;   // sorted by n descending
+         ls.cnt = cnt;
+         ls.wld = round_up(std::min(nb, maxn - p0), 4);
+         wmax = std::max(wmax, (size_t)cnt * ls.wld * ls.wld);
+         ls.trsm_prefix = prefix.size();
+         int acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int pw = std::min(nb, nt->n[f] - p0);
+            const int base = (p0 + pw) & ~1;
+            prefix.push_back(acc);
+            if (nt->m[f] > p0 + pw) acc += (nt->m[f] - base + GT_BM - 1) / GT_BM;
+         }
+         prefix.push_back(acc);
+         ls.trsm_tiles = acc;
+         ls.upd_prefix = prefix.size();
+         acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int pw = std::min(nb, nt->n[f] - p0);
+            const int base = p0 + pw;
+            prefix.push_back(acc);
+            if (nt->n[f] > base) {
+               const int TR = (nt->m[f] - base + GT_BM - 1) / GT_BM;
+               const int TC = (nt->n[f] - base + GT_BN - 1) / GT_BN;
+               for (int tj = 0; tj < TC; ++tj) acc += TR - tj;
+            }
+         }
+         prefix.push_back(acc);
+         ls.upd_tiles = acc;
+      }
+      // contribution tiles
+      lp.contrib_prefix = prefix.size();
+      int acc = 0;
+      for (int i = 0; i < lp.count; ++i) {
+         const int f = fr[i];
+         prefix.push_back(acc);
+         if (nt->m[f] > nt->n[f]) {
+            const int base = nt->n[f] & ~1;
+            const int TR = (nt->m[f] - base + GT_BM - 1) / GT_BM;
+            for (int tj = 0; tj < TR; ++tj) acc += TR - tj;
+         }
+      }
+      prefix.push_back(acc);
+      lp.contrib_tiles = acc;
+   }
+   nt->W_doubles = wmax;
+   nt->d_prefix = dev_upload(prefix);
+   nt->d_asm_work = dev_upload(asmw);
+}
+
+static void upload_geometry(NumericTree* nt) {
+   nt->d_m = dev_upload(nt->m); nt->d_n = dev_upload(nt->n);
+   nt->d_ldl = dev_upload(nt->ldl); nt->d_ldc = dev_upload(nt->ldc);
+   nt->d_loff = dev_upload(nt->loff); nt->d_coff = dev_upload(nt->coff);
+   SymbolicTree* st = nt->st;
+   DevTree& T = nt->T;
+   T.m = nt->d_m; T.n = nt->d_n; T.ldl = nt->d_ldl; T.ldc = nt->d_ldc;
+   T.loff = nt->d_loff; T.coff = nt->d_coff; T.cmapoff = st->d_cmapoff;
+   T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
+   T.L = nt->d_L; T.C = nt->d_C;
+}
+
+// Issue the whole posdef factorization on nt->stream (captured into a graph).
+static void issue_posdef(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   cudaStream_t s = nt->stream;
+   const DevTree& T = nt->T;
+   const int nb = nt->nb;
+   long launches = 0;
+   CU_TRY(cudaMemsetAsync(nt->d_L, 0, nt->L_doubles * sizeof(double), s));
+   CU_TRY(cudaMemsetAsync(nt->d_fail, 0, sizeof(int), s));
+   CU_TRY(cudaMemsetAsync(nt->d_fail + 1, 0x7f, sizeof(int), s));
+   if (st->nent > 0) {
+      const int blocks = (int)std::min<long>((st->nent + 255) / 256, 148 * 16);
+      k_scatter_a<<<blocks, 256, 0, s>>>(T, st->nent, st->d_nlist, st->d_anode, st->d_nrow, st->d_ncol,
+                                         nt->d_aval, nt->d_scaling, st->d_rlist, st->d_rptr);
+      ++launches;
+   }
+   for (size_t l = 0; l < nt->levels.size(); ++l) {
+      const LevelPlan& lp = nt->levels[l];
+      const int* d_fr = st->d_level_nodes + lp.first;
+      if (lp.max_children > 0) {
+         k_zero_contrib<<<dim3(16, lp.count), 256, 0, s>>>(T, d_fr);
+         ++launches;
+         for (auto& w : lp.asm_work) {
+            if (w.second == 0) continue;
+            k_assemble<<<w.second, 256, 0, s>>>(T, nt->d_asm_work + w.first);
+            ++launches;
+         }
+      }
+      for (size_t si = 0; si < lp.steps.size(); ++si) {
+         const LevelStep& ls = lp.steps[si];
+         k_potrf_inv<<<ls.cnt, PF_THREADS, PF_SMEM_BYTES, s>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         ++launches;
+         if (ls.trsm_tiles > 0) {
+            TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
+            k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld);
+            ++launches;
+         }
+         if (ls.upd_tiles > 0) {
+            TileBatch b{d_fr, nt->d_prefix + ls.upd_prefix, ls.cnt};
+            k_gemm_batched<<<ls.upd_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, (int)si, nb, nullptr, 0);
+            ++launches;
+         }
+      }
+      if (lp.contrib_tiles > 0) {
+         TileBatch b{d_fr, nt->d_prefix + lp.contrib_prefix, lp.count};
+         k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0);
+         ++launches;
+      }
+   }
+   CU_TRY(cudaGetLastError());
+   nt->launches = launches;
+}
+
+static void set_kernel_attributes() {
+   static bool done = false;
+   if (done) return;
+   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
+   done = true;
+}
+
+static void load_values(NumericTree* nt, const double* aval, const double* scaling) {
+   SymbolicTree* st = nt->st;
+   // number of values referenced = max src index; the caller's array covers ptr[n]-1 entries,
+   // which equals nent for a full-rank analysis.  Copy exactly what the map references.
+   cudaPointerAttributes attr{};
+   bool on_dev = false;
+   if (cudaPointerGetAttributes(&attr, aval) == cudaSuccess)
+      on_dev = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+   else
+      cudaGetLastError();
+   auto t0 = std::chrono::steady_clock::now();
+   CU_TRY(cudaMemcpyAsync(nt->d_aval, aval, nt->aval_count * sizeof(double),
+                          on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, nt->stream));
+   if (scaling) {
+      if (!nt->d_scaling) CU_TRY(cudaMalloc(&nt->d_scaling, std::max(st->n, 1) * sizeof(double)));
+      CU_TRY(cudaMemcpyAsync(nt->d_scaling, scaling, st->n * sizeof(double), cudaMemcpyDefault, nt->stream));
+   }
+   CU_TRY(cudaStreamSynchronize(nt->stream));
+   nt->t_h2d = on_dev ? 0.0 : std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
+   CU_TRY(cudaEventRecord(nt->ev0, nt->stream));
+   CU_TRY(cudaGraphLaunch(nt->graph, nt->stream));
+   CU_TRY(cudaEventRecord(nt->ev1, nt->stream));
+   int fail[2] = {0, 0};
+   CU_TRY(cudaMemcpyAsync(fail, nt->d_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, nt->stream));
+   CU_TRY(cudaStreamSynchronize(nt->stream));
+   float ms = 0;
+   CU_TRY(cudaEventElapsedTime(&ms, nt->ev0, nt->ev1));
+   nt->t_device = ms * 1e-3;
+   *stats = sylver_inform_c{};
+   int maxfront = 0;
+   for (int f = 0; f < nt->st->nnodes; ++f) maxfront = std::max(maxfront, nt->m[f]);
+   stats->maxfront = maxfront;
+   if (fail[0]) stats->flag = SYLVER_ERROR_NOT_POS_DEF;
+}
+
+NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* aval, const double* scaling,
+                                 const sylver_options_c* options, sylver_inform_c* stats) {
+   NumericTree* nt = nullptr;
+   auto w0 = std::chrono::steady_clock::now();
+   try {
+      if (device_count() == 0) throw CudaFailure{(int)cudaErrorNoDevice};
+      set_kernel_attributes();
+      symbolic_tree_upload(st);
+      nt = new NumericTree();
+      nt->st = st;
+      nt->posdef = posdef;
+      nt->opt = *options;
+      nt->nb = 128;
+      CU_TRY(cudaStreamCreateWithFlags(&nt->stream, cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreate(&nt->ev0));
+      CU_TRY(cudaEventCreate(&nt->ev1));
+      CU_TRY(cudaMalloc(&nt->d_fail, 4 * sizeof(int)));
+      // values: the map references entries 1..max(src)
+      nt->aval_count = (size_t)st->nval;
+      CU_TRY(cudaMalloc(&nt->d_aval, std::max<size_t>(nt->aval_count, 1) * sizeof(double)));
+      if (!posdef) throw CudaFailure{-98};   // indefinite path is issued by engine_indef.cu
+      build_posdef_plan(nt);
+      CU_TRY(cudaMalloc(&nt->d_L, nt->L_doubles * sizeof(double)));
+      CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
+      CU_TRY(cudaMalloc(&nt->d_W, nt->W_doubles * sizeof(double)));
+      upload_geometry(nt);
+      // capture the launch sequence once
+      cudaGraph_t g = nullptr;
+      CU_TRY(cudaStreamBeginCapture(nt->stream, cudaStreamCaptureModeThreadLocal));
+      issue_posdef(nt);
+      CU_TRY(cudaStreamEndCapture(nt->stream, &g));
+      CU_TRY(cudaGraphInstantiate(&nt->graph, g, 0));
+      CU_TRY(cudaGraphDestroy(g));
+      load_values(nt, aval, scaling);
+      run_posdef(nt, stats);
+   } catch (CudaFailure& e) {
+      *stats = sylver_inform_c{};
+      stats->flag = (e.code == -98) ? SYLVER_ERROR_UNIMPLEMENTED : SYLVER_ERROR_CUDA_UNKNOWN;
+      cudaGetLastError();
+      if (nt) numeric_tree_destroy(nt);
+      return nullptr;
+   } catch (std::bad_alloc&) {
+      *stats = sylver_inform_c{};
+      stats->flag = SYLVER_ERROR_ALLOCATION;
+      if (nt) numeric_tree_destroy(nt);
+      return nullptr;
+   }
+   nt->t_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+   return nt;
+}
+
+void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* scaling, sylver_inform_c* stats) {
+   auto w0 = std::chrono::steady_clock::now();
+   try {
+      load_values(nt, aval, scaling);
+      run_posdef(nt, stats);
+   } catch (CudaFailure&) {
+      *stats = sylver_inform_c{};
+      stats->flag = SYLVER_ERROR_CUDA_UNKNOWN;
+   }
+   nt->t_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+}
+
+void numeric_tree_destroy(NumericTree* nt) {
+   if (!nt) return;
+   if (nt->graph) cudaGraphExecDestroy(nt->graph);
+   cudaFree(nt->d_m); cudaFree(nt->d_n); cudaFree(nt->d_ldl); cudaFree(nt->d_ldc);
+   cudaFree(nt->d_loff); cudaFree(nt->d_coff); cudaFree(nt->d_L); cudaFree(nt->d_C);
+   cudaFree(nt->d_W); cudaFree(nt->d_aval); cudaFree(nt->d_scaling); cudaFree(nt->d_fail);
+   cudaFree(nt->d_prefix); cudaFree(nt->d_asm_work); cudaFree(nt->d_xw); cudaFree(nt->d_xwoff);
+   cudaFree(nt->d_child_ptr); cudaFree(nt->d_child_list);
+   if (nt->ev0) cudaEventDestroy(nt->ev0);
+   if (nt->ev1) cudaEventDestroy(nt->ev1);
+   if (nt->stream) cudaStreamDestroy(nt->stream);
+   delete nt;
+}
+
+void numeric_tree_timings(const NumericTree* nt, double* out4) {
+   out4[0] = nt->t_device;
+   out4[1] = nt->t_h2d;
+   out4[2] = nt->t_wall;
+   out4[3] = (double)nt->launches;
+}
+
+int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib) {
+   if (node < 0 || node >= nt->st->nnodes) return -1;
+   const int mm = nt->m[node], nn = nt->n[node];
+   if (m) *m = mm;
+   if (n) *n = nn;
+   try {
+      if (l)
+         CU_TRY(cudaMemcpy2D(l, (size_t)mm * sizeof(double), nt->d_L + nt->loff[node],
+                             (size_t)nt->ldl[node] * sizeof(double), (size_t)mm * sizeof(double), nn,
+                             cudaMemcpyDeviceToHost));
+      const int k = mm - nn;
+      if (contrib && k > 0)
+         CU_TRY(cudaMemcpy2D(contrib, (size_t)k * sizeof(double), nt->d_C + nt->coff[node],
+                             (size_t)nt->ldc[node] * sizeof(double), (size_t)k * sizeof(double), k,
+                             cudaMemcpyDeviceToHost));
+   } catch (CudaFailure&) {
+      return -51;
+   }
+   return 0;
+}
+
+// ===========================================================================
+// Triangular solves (reference src/NumericTree.hxx:408-532,
+// src/NumericTreePosdef.hxx:355-420): level-batched, one CTA per front.
+// ===========================================================================
+static void ensure_solve_workspace(NumericTree* nt) {
+   if (nt->d_xw) return;
+   SymbolicTree* st = nt->st;
+   nt->xwoff.resize(st->nnodes + 1);
+   long off = 0;
+   for (int f = 0; f < st->nnodes; ++f) {
+      nt->xwoff[f] = off;
+      off += nt->m[f];
+   }
+   nt->xwoff[st->nnodes] = off;
+   CU_TRY(cudaMalloc(&nt->d_xw, std::max<long>(off, 1) * sizeof(double)));
+   nt->d_xwoff = dev_upload(nt->xwoff);
+   nt->d_child_ptr = dev_upload(st->child_ptr);
+   nt->d_child_list = dev_upload(st->child_list);
+}
+
+int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int ldx) {
+   NumericTree* nt = const_cast<NumericTree*>(cnt);
+   SymbolicTree* st = nt->st;
+   try {
+      ensure_solve_workspace(nt);
+      cudaPointerAttributes attr{};
+      bool on_dev = false;
+      if (cudaPointerGetAttributes(&attr, x) == cudaSuccess)
+         on_dev = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+      else
+         cudaGetLastError();
+      double* dx = x;
+      if (!on_dev) {
+         CU_TRY(cudaMalloc(&dx, (size_t)ldx * nrhs * sizeof(double)));
+         CU_TRY(cudaMemcpyAsync(dx, x, (size_t)ldx * nrhs * sizeof(double), cudaMemcpyHostToDevice, nt->stream));
+      }
+      SolveArgs a{};
+      a.T = nt->T;
+      a.rlist = st->d_rlist;
+      a.rptr = st->d_rptr;
+      a.xwoff = nt->d_xwoff;
+      a.xw = nt->d_xw;
+      a.child_ptr = nt->d_child_ptr;
+      a.child_list = nt->d_child_list;
+      a.posdef = nt->posdef ? 1 : 0;
+      const bool do_fwd = (job == 0 || job == 1);
+      const bool do_bwd = (job == 0 || job == 3 || job == 4);
+      for (int r = 0; r < nrhs; ++r) {
+         a.x = dx + (size_t)r * ldx;
+         if (do_fwd)
+            for (int l = 0; l < st->nlevels; ++l) {
+               const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;
+               k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, st->d_level_nodes + first);
+            }
+         if (do_bwd)
+            for (int l = st->nlevels - 1; l >= 0; --l) {
+               const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;
+               k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, st->d_level_nodes + first);
+            }
+      }
+      CU_TRY(cudaGetLastError());
+      if (!on_dev) {
+         CU_TRY(cudaMemcpyAsync(x, dx, (size_t)ldx * nrhs * sizeof(double), cudaMemcpyDeviceToHost, nt->stream));
+         CU_TRY(cudaStreamSynchronize(nt->stream));
+         CU_TRY(cudaFree(dx));
+      } else {
+         CU_TRY(cudaStreamSynchronize(nt->stream));
+      }
+   } catch (CudaFailure&) {
+      return SYLVER_ERROR_CUDA_UNKNOWN;
+   }
+   return SYLVER_SUCCESS;
+}
+
+}  // namespace sylver_b200

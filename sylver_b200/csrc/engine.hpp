@@ -1,0 +1,72 @@
+// Host side of the B200 numeric factorization engine: the assembly-tree plan
+// (SymbolicTree) and the level-scheduled numeric factorization (NumericTree)
+// that replace the reference's SymbolicTree / NumericTree[Posdef] + StarPU
+// (src/SymbolicTree.cxx, src/NumericTree.hxx:54-406, src/NumericTreePosdef.hxx:42-353).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/sylver_b200.h"
+
+namespace sylver_b200 {
+
+struct SymbolicTree {
+   int n = 0;
+   int nnodes = 0;
+   long nent = 0;                       // entries of A mapped into fronts
+   long nval = 0;                       // extent of the caller's value array (max src index)
+   long num_flops = 0;
+   // ---- host copies (0-based) ----
+   std::vector<int> nrow, ncol, parent, nchild, level;
+   std::vector<int> child_ptr, child_list;   // children in decreasing index order (reference order)
+   std::vector<long> rptr;                   // 0-based offsets into rlist
+   std::vector<int> rlist;                   // 1-based row indices (as given)
+   std::vector<long> cmapoff;                // per node, offset into cmap
+   std::vector<int> cmap;                    // child contribution row -> parent local row (0-based)
+   std::vector<int> level_ptr, level_nodes;  // fronts grouped by level (height), ncol descending
+   int nlevels = 0;
+   // ---- device resident static data ----
+   int* d_rlist = nullptr;
+   long* d_rptr = nullptr;       // 1-based values as given (nnodes+1)
+   long* d_nlist = nullptr;
+   int* d_anode = nullptr;
+   int* d_nrow = nullptr;
+   int* d_ncol = nullptr;
+   int* d_parent = nullptr;
+   int* d_nchild = nullptr;
+   int* d_cmap = nullptr;
+   long* d_cmapoff = nullptr;
+   int* d_level_nodes = nullptr;
+   bool on_device = false;
+   int device = 0;
+
+   ~SymbolicTree();
+};
+
+// Builds the plan.  Returns nullptr and sets *flag (<0) on failure.  The device
+// copy is made lazily (first numeric factorization) so that symbolic parity can
+// be tested without a GPU.
+SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int* sparent,
+                                   const long* rptr, const int* rlist, const long* nptr,
+                                   const long* nlist, int* flag);
+
+struct NumericTree;
+
+NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* aval, const double* scaling,
+                                 const sylver_options_c* options, sylver_inform_c* stats);
+// Re-run the factorization with new values on an existing tree (same plan).
+void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* scaling,
+                           sylver_inform_c* stats);
+void numeric_tree_destroy(NumericTree* nt);
+// job: 1 fwd, 2 diag, 3 bwd, 4 diag+bwd, 0 all.  x host or device, already permuted.
+int numeric_tree_solve(const NumericTree* nt, int job, int nrhs, double* x, int ldx);
+void numeric_tree_timings(const NumericTree* nt, double* out4);
+bool numeric_tree_posdef(const NumericTree* nt);
+// Debug / test access: copy one front's L panel (m x n, ld m) and contribution
+// ((m-n)^2, ld m-n) to host buffers (either may be null). Returns 0 or <0.
+int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib);
+
+int device_count();
+
+}  // namespace sylver_b200

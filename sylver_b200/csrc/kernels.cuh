@@ -1,0 +1,470 @@
+// Device kernels of the B200 multifrontal numeric factorization (sm_100a).
+//
+// Layout conventions (see DESIGN.md "Data layout in HBM"):
+//   * Every front f owns an m x n column-major panel `L + loff[f]` with leading
+//     dimension ldl[f] (multiple of 4 doubles, so every column starts 32 B
+//     aligned and one element past an odd m is addressable padding).
+//   * Its generated element (contribution block) is a dense (m-n) x (m-n)
+//     lower triangle at `C + coff[f]`, leading dimension ldc[f].
+//   * Per-edge assembly maps cmap (child contribution row -> parent local row)
+//     are device resident and were built at symbolic-tree creation.
+//
+// Reference functions each kernel replaces are cited at the kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sylver_b200 {
+
+// Device view of the assembly tree (structure-of-arrays, one entry per front).
+struct DevTree {
+   const int* m;         // rows of the front (nrow + ndelay_in)
+   const int* n;         // fully-summed columns (ncol + ndelay_in)
+   const int* ldl;       // leading dimension of the L panel
+   const int* ldc;       // leading dimension of the contribution block
+   const long* loff;     // offset (doubles) of the L panel in the factor arena
+   const long* coff;     // offset (doubles) of the contribution block
+   const long* cmapoff;  // offset into cmap of this front's contribution rows
+   const int* parent;    // parent front (nnodes = virtual root)
+   const int* nchild;    // number of children
+   const int* cmap;      // concatenated child->parent row maps (0-based)
+   double* L;            // factor arena
+   double* C;            // contribution arena
+};
+
+// ---------------------------------------------------------------------------
+// PTX helpers: FP64 tensor-core MMA, mbarrier, TMA bulk copy
+// ---------------------------------------------------------------------------
+// D(8x8) += A(8x4) * B(4x8); fragment layout (lane = 4*g + t):
+//   a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].   SASS: DMMA.8x8x4
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0), "+d"(c1)
+                : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+   return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+// (SASS: UBLKCP).  dst/src 16 B aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+   asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+         smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Tiled DMMA  C(128x128) (+)= -A(128xK) * B(128xK)^T   ("NT" rank-K update)
+//
+// Replaces update_block / update_contrib_block / form_contrib
+// (reference src/kernels/factor.hxx:149-263, src/kernels/factor_indef.hxx:23-49,
+// 201-342; GPU variants src/StarPU/cuda/kernels.hxx:45-182) and, with the
+// inverted diagonal block as B, solve_block (src/kernels/factor.hxx:95-138).
+//
+// Both operands are column-major panels (row index contiguous), staged into
+// shared memory k-column by k-column with TMA bulk copies through a 4-stage
+// mbarrier pipeline by one producer warp; 8 consumer warps (4 x 2, 32 x 64 per
+// warp) issue DMMA.8x8x4 from conflict-free padded shared memory.
+// ---------------------------------------------------------------------------
+constexpr int GT_BM = 128;             // tile rows
+constexpr int GT_BN = 128;             // tile cols
+constexpr int GT_KT = 16;              // k-columns per stage
+constexpr int GT_LDS = 132;            // padded smem row stride (132 mod 16 == 4: conflict free)
+constexpr int GT_STAGES = 4;
+constexpr int GT_CONSUMERS = 8;        // warps
+constexpr int GT_THREADS = (GT_CONSUMERS + 1) * 32;
+constexpr size_t GT_STAGE_DOUBLES = 2 * GT_KT * GT_LDS;
+constexpr size_t GT_SMEM_BYTES = GT_STAGES * GT_STAGE_DOUBLES * sizeof(double) + 2 * GT_STAGES * sizeof(uint64_t);
+
+struct GemmTile {
+   const double* A;   // first row of the A operand tile, k = 0 column
+   const double* B;   // first row of the B operand tile, k = 0 column
+   int lda, ldb;      // column strides (doubles)
+   int arows, brows;  // valid rows (<=128) in each operand tile (rounded up to even inside)
+   int K;             // depth
+};
+
+// Runs the pipeline; on return acc[i][j][0..1] holds the 32x64 warp tile:
+// rows wm*32 + i*8 + g, cols wn*64 + j*8 + 2t + {0,1}.  Producer warp returns with acc untouched.
+__device__ __forceinline__ void gemm_tile_mainloop(const GemmTile& t, double* smem, double (&acc)[4][8][2]) {
+   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_DOUBLES);
+   uint64_t* empty = full + GT_STAGES;
+   const int warp = threadIdx.x >> 5;
+   const int lane = threadIdx.x & 31;
+   if (threadIdx.x == 0) {
+      for (int s = 0; s < GT_STAGES; ++s) {
+         mbar_init(&full[s], 1);
+         mbar_init(&empty[s], GT_CONSUMERS);
+      }
+      mbar_fence_init();
+   }
+   __syncthreads();
+   const int nk = (t.K + GT_KT - 1) / GT_KT;
+   const bool same = (t.A == t.B) && (t.lda == t.ldb);   // diagonal tile: stage the panel once
+   if (warp == GT_CONSUMERS) {
+      // ===== producer warp: lane l < 16 copies A column l, lane 16+l copies B column l =====
+      const uint32_t abytes = (uint32_t)(((t.arows + 1) & ~1) * sizeof(double));
+      const uint32_t bbytes = (uint32_t)(((t.brows + 1) & ~1) * sizeof(double));
+      for (int kb = 0; kb < nk; ++kb) {
+         const int s = kb % GT_STAGES;
+         const uint32_t ph = (kb / GT_STAGES) & 1;
+         mbar_wait(&empty[s], ph ^ 1);
+         const int k0 = kb * GT_KT;
+         const int kv = min(GT_KT, t.K - k0);           // valid k-columns in this stage
+         double* As = smem + s * GT_STAGE_DOUBLES;
+         double* Bs = As + GT_KT * GT_LDS;
+         const int kc = lane & 15;
+         const bool isB = lane >= 16;
+         if (kc >= kv && kc < ((kv + 3) & ~3)) {
+            // zero-fill the tail of a partial k-group (generic proxy; ordered by the arrive below)
+            double* dst = (isB ? Bs : As) + kc * GT_LDS;
+            if (!(isB && same))
+               for (int r = 0; r < GT_BM; ++r) dst[r] = 0.0;
+         }
+         __syncwarp();
+         if (lane == 0) mbar_expect_tx(&full[s], kv * (abytes + (same ? 0u : bbytes)));
+         __syncwarp();
+         if (kc < kv) {
+            if (!isB)
+               tma_bulk_g2s(As + kc * GT_LDS, t.A + (size_t)(k0 + kc) * t.lda, abytes, &full[s]);
+            else if (!same)
+               tma_bulk_g2s(Bs + kc * GT_LDS, t.B + (size_t)(k0 + kc) * t.ldb, bbytes, &full[s]);
+         }
+      }
+      return;
+   }
+   // ===== consumer warps =====
+   const int wm = warp & 3, wn = warp >> 2;
+   const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+   for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+   for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % GT_STAGES;
+      const uint32_t ph = (kb / GT_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      const double* As = smem + s * GT_STAGE_DOUBLES;
+      const double* Bs = same ? As : As + GT_KT * GT_LDS;
+      const int kv = min(GT_KT, t.K - kb * GT_KT);
+      const int kg = (kv + 3) >> 2;
+      const double* ap = As + tq * GT_LDS + wm * 32 + g;
+      const double* bp = Bs + tq * GT_LDS + wn * 64 + g;
+#pragma unroll 1
+      for (int k4 = 0; k4 < kg; ++k4) {
+         double a[4], b[8];
+#pragma unroll
+         for (int i = 0; i < 4; ++i) a[i] = ap[i * 8];
+#pragma unroll
+         for (int j = 0; j < 8; ++j) b[j] = bp[j * 8];
+#pragma unroll
+         for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+         ap += 4 * GT_LDS;
+         bp += 4 * GT_LDS;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+   }
+}
+
+// Work descriptor of one batched launch: the participating fronts and an
+// exclusive prefix sum of their tile counts.
+struct TileBatch {
+   const int* fronts;   // [cnt]
+   const int* prefix;   // [cnt+1]
+   int cnt;
+};
+
+__device__ __forceinline__ int find_front(const TileBatch& b, int item) {
+   int lo = 0, hi = b.cnt;          // prefix[lo] <= item < prefix[hi]
+   while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (b.prefix[mid] <= item) lo = mid; else hi = mid;
+   }
+   return lo;
+}
+
+// mode 0: trailing update inside the L panel after block column [p0, p0+pw):
+//         L[r][c] -= sum_k L[r][k] L[c][k],  c in [p0+pw, n), r in [c, m)
+// mode 1: contribution block:  C[r-n][c-n] = beta*C - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
+// mode 2: panel solve with the inverted diagonal block W (pw x pw, ld 128):
+//         L[r][p0+c] = sum_k L[r][p0+k] W[c][k],  r in [p0+pw, m)
+// nb is the block-column width; `step` the block column index.
+static __global__ void __launch_bounds__(GT_THREADS, 1)
+k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld) {
+   extern __shared__ __align__(128) double smem[];
+   const int item = blockIdx.x;
+   const int fi = find_front(batch, item);
+   const int f = batch.fronts[fi];
+   int local = item - batch.prefix[fi];
+   const int m = T.m[f], n = T.n[f], ldl = T.ldl[f];
+   double* Lf = T.L + T.loff[f];
+   const int p0 = step * nb;
+   const int pw = min(nb, n - p0);
+
+   GemmTile t;
+   int i0, j0;          // absolute front row / column of the tile origin
+   if (mode == 2) {
+      // tile origin rounded down to an even row so the TMA source stays 16 B aligned
+      i0 = ((p0 + pw) & ~1) + local * GT_BM;
+      j0 = p0;
+      t.A = Lf + (size_t)p0 * ldl + i0;
+      t.lda = ldl;
+      t.arows = min(GT_BM, m - i0);
+      t.B = W + (size_t)fi * wld * wld;   // slot fi of this launch's inverse buffer
+      t.ldb = wld;
+      t.brows = pw;
+      t.K = pw;
+   } else {
+      const int base = (mode == 0) ? (p0 + pw) : (n & ~1);
+      const int cend = (mode == 0) ? n : m;
+      const int TR = (m - base + GT_BM - 1) / GT_BM;
+      const int TC = (cend - base + GT_BN - 1) / GT_BN;
+      int tj = 0;
+      while (tj < TC && local >= TR - tj) { local -= TR - tj; ++tj; }
+      const int ti = tj + local;
+      i0 = base + ti * GT_BM;
+      j0 = base + tj * GT_BN;
+      const int kbeg = (mode == 0) ? p0 : 0;
+      t.K = (mode == 0) ? pw : n;
+      t.A = Lf + (size_t)kbeg * ldl + i0;
+      t.B = Lf + (size_t)kbeg * ldl + j0;
+      t.lda = t.ldb = ldl;
+      t.arows = min(GT_BM, m - i0);
+      t.brows = min(GT_BN, m - j0);
+   }
+   double acc[4][8][2];
+   gemm_tile_mainloop(t, smem, acc);
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   if (warp == GT_CONSUMERS) return;
+   const int wm = warp & 3, wn = warp >> 2, g = lane >> 2, tq = lane & 3;
+   if (mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h) {
+            const int c = wn * 64 + j * 8 + 2 * tq + h;
+            if (c >= pw) continue;
+            double* col = Lf + (size_t)(p0 + c) * ldl;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const int r = i0 + wm * 32 + i * 8 + g;
+               if (r < m && r >= p0 + pw) col[r] = acc[i][j][h];
+            }
+         }
+      return;
+   }
+   if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h) {
+            const int c = j0 + wn * 64 + j * 8 + 2 * tq + h;
+            if (c >= n) continue;
+            double* col = Lf + (size_t)c * ldl;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const int r = i0 + wm * 32 + i * 8 + g;
+               if (r < m && r >= c) col[r] -= acc[i][j][h];
+            }
+         }
+      return;
+   }
+   {
+      double* Cf = T.C + T.coff[f];
+      const int ldc = T.ldc[f];
+      const bool accum = T.nchild[f] > 0;     // children were extend-added before the factorization
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h) {
+            const int c = j0 + wn * 64 + j * 8 + 2 * tq + h;
+            if (c < n || c >= m) continue;
+            double* col = Cf + (size_t)(c - n) * ldc - n;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const int r = i0 + wm * 32 + i * 8 + g;
+               if (r < m && r >= c) col[r] = accum ? col[r] - acc[i][j][h] : -acc[i][j][h];
+            }
+         }
+   }
+}
+
+// ---------------------------------------------------------------------------
+// A -> front scatter.  Replaces init_a_block / init_node
+// (reference src/kernels/assemble.hxx:162-214): dest = col*nrow + row (1-based),
+// rows >= ncol shifted by ndelay_in, optional symmetric scaling.
+// ---------------------------------------------------------------------------
+static __global__ void k_scatter_a(DevTree T, long nent, const long* __restrict__ nlist,
+                            const int* __restrict__ anode, const int* __restrict__ nrow0,
+                            const int* __restrict__ ncol0, const double* __restrict__ aval,
+                            const double* __restrict__ scaling, const int* __restrict__ rlist,
+                            const long* __restrict__ rptr) {
+   for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
+      const int f = anode[e];
+      const long src = nlist[2 * e] - 1;
+      const long dest = nlist[2 * e + 1] - 1;
+      const int nrow = nrow0[f];
+      const int c = (int)(dest / nrow);
+      int r = (int)(dest - (long)c * nrow);
+      double v = aval[src];
+      if (scaling) {
+         const int* rl = rlist + (rptr[f] - 1);
+         v *= scaling[rl[r] - 1] * scaling[rl[c] - 1];
+      }
+      const int ndelay = T.n[f] - ncol0[f];
+      if (r >= ncol0[f]) r += ndelay;
+      T.L[T.loff[f] + (size_t)c * T.ldl[f] + r] = v;
+   }
+}
+
+// Zero the contribution blocks of fronts that will receive children.
+static __global__ void k_zero_contrib(DevTree T, const int* __restrict__ fronts) {
+   const int f = fronts[blockIdx.y];
+   if (T.nchild[f] == 0) return;
+   const int k = T.m[f] - T.n[f];
+   const size_t tot = (size_t)k * T.ldc[f];
+   double* Cf = T.C + T.coff[f];
+   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+      Cf[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// Extend-add of one child's contribution block into its parent front.
+// Replaces assemble_block / assemble_contrib_block (reference
+// src/kernels/assemble.hxx:230-286,343-517) with a single pass driven by the
+// precomputed device map: entry (i,j) of the child's block goes to parent
+// (cmap[i], cmap[j]) -- into the L panel when cmap[j] < n_parent, else into the
+// parent's contribution block.  One launch handles the q-th child of every
+// parent of a level, so contributions are summed in a fixed (reference) order.
+// work item = (child, first column of a 32-column chunk); warp w takes columns
+// w, w+8, ...; lanes stride over rows (coalesced reads of the child block).
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* __restrict__ work) {
+   const int2 w = work[blockIdx.x];
+   const int c = w.x;
+   const int p = T.parent[c];
+   const int k = T.m[c] - T.n[c];
+   const int* cm = T.cmap + T.cmapoff[c];
+   const double* src = T.C + T.coff[c];
+   const int ldcc = T.ldc[c];
+   const int pn = T.n[p], pldl = T.ldl[p], pldc = T.ldc[p];
+   double* PL = T.L + T.loff[p];
+   double* PC = T.C + T.coff[p];
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int jend = min(k, w.y + 32);
+   for (int j = w.y + warp; j < jend; j += 8) {
+      const int rj = cm[j];
+      const double* s = src + (size_t)j * ldcc;
+      double* dcol = (rj < pn) ? PL + (size_t)rj * pldl : PC + (size_t)(rj - pn) * pldc - pn;
+      for (int i = j + lane; i < k; i += 32) dcol[cm[i]] += s[i];
+   }
+}
+
+// ---------------------------------------------------------------------------
+// Cholesky of one diagonal block (pw <= 128) per CTA, plus its explicit
+// inverse W = L_jj^{-1} (lower, ld 128) used by the DMMA panel solve.
+// Replaces factorize_diag_block (reference src/kernels/factor.hxx:34-88; LAPACK
+// dpotrf there).  A non-positive pivot records (front, column) in `fail`.
+// ---------------------------------------------------------------------------
+constexpr int PF_LD = 129;
+constexpr int PF_THREADS = 512;
+constexpr size_t PF_SMEM_BYTES = ((size_t)2 * 128 * PF_LD + 128) * sizeof(double);
+
+static __global__ void __launch_bounds__(PF_THREADS, 1)
+k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double* __restrict__ W, int wld,
+            int* fail) {
+   extern __shared__ __align__(16) double sm[];
+   double* S = sm;                    // S[r + c*PF_LD]
+   double* V = sm + 128 * PF_LD;      // inverse
+   double* rd = V + 128 * PF_LD;      // reciprocal diagonal
+   const int f = fronts[blockIdx.x];
+   const int n = T.n[f], ldl = T.ldl[f];
+   const int p0 = step * nb;
+   const int pw = min(nb, n - p0);
+   double* A = T.L + T.loff[f] + (size_t)p0 * ldl + p0;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   constexpr int NW = PF_THREADS / 32;
+   for (int c = warp; c < pw; c += NW)
+      for (int r = lane; r < pw; r += 32) S[r + c * PF_LD] = (r >= c) ? A[(size_t)c * ldl + r] : 0.0;
+   __syncthreads();
+   // right-looking Cholesky, 2 barriers per column; warp w updates columns k+1+w, k+1+w+NW, ...
+   for (int k = 0; k < pw; ++k) {
+      const double akk = S[k + k * PF_LD];
+      const bool ok = akk > 0.0;
+      if (!ok && tid == 0) {
+         atomicExch(&fail[0], 1);
+         atomicMin(&fail[1], f);
+      }
+      const double d = ok ? sqrt(akk) : 1.0;
+      const double rinv = 1.0 / d;
+      __syncthreads();
+      for (int r = k + tid; r < pw; r += PF_THREADS) S[r + k * PF_LD] = (r == k) ? d : S[r + k * PF_LD] * rinv;
+      __syncthreads();
+      for (int c = k + 1 + warp; c < pw; c += NW) {
+         const double lck = S[c + k * PF_LD];
+         for (int r = c + lane; r < pw; r += 32) S[r + c * PF_LD] -= S[r + k * PF_LD] * lck;
+      }
+   }
+   __syncthreads();
+   for (int c = warp; c < pw; c += NW)
+      for (int r = c + lane; r < pw; r += 32) A[(size_t)c * ldl + r] = S[r + c * PF_LD];
+   for (int i = tid; i < pw; i += PF_THREADS) rd[i] = 1.0 / S[i + i * PF_LD];
+   __syncthreads();
+   // Inverse by forward substitution: 4 lanes cooperate on one column j of V (L v = e_j),
+   // splitting each dot product; no block barrier is needed inside a column.
+   {
+      const int q = tid & 3;
+      for (int j = tid >> 2; j < 128; j += PF_THREADS / 4) {
+         if (j >= pw) continue;     // whole quad skips together (same j)
+         for (int i = q; i < j; i += 4) V[i + j * PF_LD] = 0.0;
+         if (q == 0) V[j + j * PF_LD] = rd[j];
+         __syncwarp(0xFu << (lane & ~3));
+         for (int i = j + 1; i < pw; ++i) {
+            double s = 0.0;
+            for (int kk = j + q; kk < i; kk += 4) s += S[i + kk * PF_LD] * V[kk + j * PF_LD];
+            s += __shfl_xor_sync(0xFu << (lane & ~3), s, 1);
+            s += __shfl_xor_sync(0xFu << (lane & ~3), s, 2);
+            if (q == 0) V[i + j * PF_LD] = -s * rd[i];
+            __syncwarp(0xFu << (lane & ~3));
+         }
+      }
+   }
+   __syncthreads();
+   double* Wf = W + (size_t)blockIdx.x * wld * wld;
+   for (int c = warp; c < wld; c += NW)
+      for (int r = lane; r < wld; r += 32) Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[r + c * PF_LD] : 0.0;
+}
+
+}  // namespace sylver_b200

@@ -1,0 +1,120 @@
+// Triangular-solve kernels: level-batched, one CTA per front, deterministic
+// (children's update vectors are added by the parent in a fixed order instead
+// of atomics).  Replaces NumericTree::solve_fwd / solve_diag_bwd and the
+// per-front ldlt_app_solve_* / cholesky_solve_* (reference
+// src/NumericTree.hxx:408-532, spral/src/ssids/cpu/kernels/ldlt_app.cxx:2536-2590).
+#pragma once
+#include "kernels.cuh"
+
+namespace sylver_b200 {
+
+constexpr int SOLVE_THREADS = 512;
+
+struct SolveArgs {
+   DevTree T;
+   const int* rlist;        // 1-based global row indices, concatenated
+   const long* rptr;        // 1-based offsets into rlist
+   const int* perm;         // indefinite: per-front pivot permutation (concatenated, permoff), 1-based
+   const long* permoff;
+   const double* D;         // indefinite: D^-1 storage, 2 per column, at doff[f]
+   const long* doff;
+   const int* nelim;        // indefinite: eliminated columns per front
+   const long* xwoff;       // per-front offset into xw
+   double* xw;              // work vectors (sum of m)
+   const int* child_ptr;
+   const int* child_list;
+   double* x;               // right-hand side / solution in elimination order
+   int posdef;
+};
+
+// index of local variable i (< n) of front f in the global vector
+__device__ __forceinline__ int var_index(const SolveArgs& a, int f, int i, const int* rl) {
+   if (a.posdef) return rl[i] - 1;
+   return a.perm[a.permoff[f] + i] - 1;
+}
+
+static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_fwd(SolveArgs a, const int* __restrict__ fronts) {
+   const int f = fronts[blockIdx.x];
+   const int m = a.T.m[f], n = a.T.n[f], ldl = a.T.ldl[f];
+   const int ne = a.posdef ? n : a.nelim[f];
+   const double* L = a.T.L + a.T.loff[f];
+   double* xw = a.xw + a.xwoff[f];
+   const int* rl = a.rlist + (a.rptr[f] - 1);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   for (int i = tid; i < m; i += SOLVE_THREADS) xw[i] = (i < n) ? a.x[var_index(a, f, i, rl)] : 0.0;
+   __syncthreads();
+   for (int ci = a.child_ptr[f]; ci < a.child_ptr[f + 1]; ++ci) {
+      const int c = a.child_list[ci];
+      const int cn = a.T.n[c];
+      const int k = a.T.m[c] - cn;
+      const int* cm = a.T.cmap + a.T.cmapoff[c];
+      const double* src = a.xw + a.xwoff[c];
+      for (int i = tid; i < k; i += SOLVE_THREADS) xw[cm[i]] += src[cn + i];
+      __syncthreads();
+   }
+   for (int j0 = 0; j0 < ne; j0 += 32) {
+      const int jb = min(32, ne - j0);
+      if (warp == 0) {
+         double y = (lane < jb) ? xw[j0 + lane] : 0.0;
+         for (int k = 0; k < jb; ++k) {
+            double yk = __shfl_sync(0xffffffffu, y, k);
+            if (a.posdef) yk /= L[(size_t)(j0 + k) * ldl + j0 + k];
+            if (lane == k) y = yk;
+            if (lane > k && lane < jb) y -= L[(size_t)(j0 + k) * ldl + j0 + lane] * yk;
+         }
+         if (lane < jb) xw[j0 + lane] = y;
+      }
+      __syncthreads();
+      for (int r = j0 + jb + tid; r < m; r += SOLVE_THREADS) {
+         double s = 0.0;
+         const double* lp = L + (size_t)j0 * ldl + r;
+         for (int k = 0; k < jb; ++k) s += lp[(size_t)k * ldl] * xw[j0 + k];
+         xw[r] -= s;
+      }
+      __syncthreads();
+   }
+   for (int i = tid; i < n; i += SOLVE_THREADS) a.x[var_index(a, f, i, rl)] = xw[i];
+}
+
+static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_bwd(SolveArgs a, const int* __restrict__ fronts) {
+   const int f = fronts[blockIdx.x];
+   const int m = a.T.m[f], n = a.T.n[f], ldl = a.T.ldl[f];
+   const int ne = a.posdef ? n : a.nelim[f];
+   const double* L = a.T.L + a.T.loff[f];
+   double* xw = a.xw + a.xwoff[f];
+   const int* rl = a.rlist + (a.rptr[f] - 1);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   constexpr int NW = SOLVE_THREADS / 32;
+   const int ncol0 = (int)(a.rptr[f + 1] - a.rptr[f]) - (m - n);   // original fully-summed columns
+   for (int i = tid; i < m; i += SOLVE_THREADS)
+      xw[i] = (i < n) ? a.x[var_index(a, f, i, rl)] : a.x[rl[ncol0 + (i - n)] - 1];
+   __syncthreads();
+   const int nblk = (ne + 31) / 32;
+   for (int b = nblk - 1; b >= 0; --b) {
+      const int j0 = b * 32;
+      const int jb = min(32, ne - j0);
+      for (int kk = warp; kk < jb; kk += NW) {
+         const double* lp = L + (size_t)(j0 + kk) * ldl;
+         double s = 0.0;
+         for (int r = j0 + jb + lane; r < m; r += 32) s += lp[r] * xw[r];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+         if (lane == 0) xw[j0 + kk] -= s;
+      }
+      __syncthreads();
+      if (warp == 0) {
+         double y = (lane < jb) ? xw[j0 + lane] : 0.0;
+         for (int k = jb - 1; k >= 0; --k) {
+            double yk = __shfl_sync(0xffffffffu, y, k);
+            if (a.posdef) yk /= L[(size_t)(j0 + k) * ldl + j0 + k];
+            if (lane == k) y = yk;
+            if (lane < k) y -= L[(size_t)(j0 + lane) * ldl + j0 + k] * yk;
+         }
+         if (lane < jb) xw[j0 + lane] = y;
+      }
+      __syncthreads();
+   }
+   for (int i = tid; i < ne; i += SOLVE_THREADS) a.x[var_index(a, f, i, rl)] = xw[i];
+}
+
+}  // namespace sylver_b200
