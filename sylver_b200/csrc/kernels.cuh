@@ -400,15 +400,18 @@ static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* 
 // ---------------------------------------------------------------------------
 constexpr int PF_LD = 129;
 constexpr int PF_THREADS = 512;
-constexpr size_t PF_SMEM_BYTES = ((size_t)2 * 128 * PF_LD + 128) * sizeof(double);
+constexpr int PF_VPACK = 128 * 129 / 2;   // packed lower triangle of the inverse
+constexpr size_t PF_SMEM_BYTES = ((size_t)128 * PF_LD + PF_VPACK + 128) * sizeof(double);
+// packed column-major lower triangle: element (i,j), i >= j
+__device__ __forceinline__ int vpk(int i, int j) { return j * 128 - (j * (j - 1)) / 2 + (i - j); }
 
 static __global__ void __launch_bounds__(PF_THREADS, 1)
 k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double* __restrict__ W, int wld,
             int* fail) {
    extern __shared__ __align__(16) double sm[];
    double* S = sm;                    // S[r + c*PF_LD]
-   double* V = sm + 128 * PF_LD;      // inverse
-   double* rd = V + 128 * PF_LD;      // reciprocal diagonal
+   double* V = sm + 128 * PF_LD;      // inverse, packed lower triangle
+   double* rd = V + PF_VPACK;         // reciprocal diagonal
    const int f = fronts[blockIdx.x];
    const int n = T.n[f], ldl = T.ldl[f];
    const int p0 = step * nb;
@@ -448,15 +451,15 @@ k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double*
       const int q = tid & 3;
       for (int j = tid >> 2; j < 128; j += PF_THREADS / 4) {
          if (j >= pw) continue;     // whole quad skips together (same j)
-         for (int i = q; i < j; i += 4) V[i + j * PF_LD] = 0.0;
-         if (q == 0) V[j + j * PF_LD] = rd[j];
+         if (q == 0) V[vpk(j, j)] = rd[j];
          __syncwarp(0xFu << (lane & ~3));
          for (int i = j + 1; i < pw; ++i) {
             double s = 0.0;
-            for (int kk = j + q; kk < i; kk += 4) s += S[i + kk * PF_LD] * V[kk + j * PF_LD];
+            const double* vj = V + vpk(j, j) - j;      // vj[kk] = V(kk, j)
+            for (int kk = j + q; kk < i; kk += 4) s += S[i + kk * PF_LD] * vj[kk];
             s += __shfl_xor_sync(0xFu << (lane & ~3), s, 1);
             s += __shfl_xor_sync(0xFu << (lane & ~3), s, 2);
-            if (q == 0) V[i + j * PF_LD] = -s * rd[i];
+            if (q == 0) V[vpk(i, j)] = -s * rd[i];
             __syncwarp(0xFu << (lane & ~3));
          }
       }
@@ -464,7 +467,7 @@ k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double*
    __syncthreads();
    double* Wf = W + (size_t)blockIdx.x * wld * wld;
    for (int c = warp; c < wld; c += NW)
-      for (int r = lane; r < wld; r += 32) Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[r + c * PF_LD] : 0.0;
+      for (int r = lane; r < wld; r += 32) Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[vpk(r, c)] : 0.0;
 }
 
 }  // namespace sylver_b200
