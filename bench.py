@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- numeric-factorization throughput of the B200 engine.
+
+Contract (see the task statement): one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm
+  python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm
+
+A "step" is one numeric factorization (the spldlt_factorize call; analyse is
+excluded) of BASELINE.json's headline workload: the 3D 27-point Laplacian on a
+100^3 grid (n = 10^6, posdef Cholesky; configs[2], the largest single-GPU
+configuration the metric "fp64 numeric-factor GFLOP/s ... 3D Laplacian 100^3" is
+quoted on).  GFLOP/s = num_flops / seconds / 1e9 with the reference's own
+num_flops (spral/src/core_analyse.f90:880-892).
+
+  value : values already resident in HBM (device pointer passed through the C ABI)
+  e2e   : same call with HOST values (pinned), H2D inside the timed region and the
+          inform/flag D2H read back every step
+  roofline : the DMMA tile kernel (k_gemm_batched: trsm + update + contribution),
+          algorithmic flops / CUDA-event time, against the FP64 DMMA issue peak
+          measured in the same run (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline / --impl reference : the SSIDS CPU engine (oracle/_ref, the code
+          SyLVER delegates subtrees to) on the host cores, on a bounded sample
+          (27-point Laplacian on a smaller grid) -- the full StarPU build cannot be
+          produced here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64 numeric-factor GFLOP/s, 3D 27-point Laplacian 100^3 (n=1e6) posdef Cholesky"
+UNIT = "GFLOP/s"
+KNAMES = ["scatter", "zero", "assemble", "potrf", "trsm", "update", "contrib"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=100, help="grid side of the 27-point Laplacian")
+    ap.add_argument("--sample-grid", type=int, default=44, help="grid side of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: SSIDS CPU engine on a bounded sample
+# ----------------------------------------------------------------------------
+def run_reference_sample(grid: int, steps: int, warmup: int):
+    cores = host_cores()
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    import numpy as np
+    import sylver_b200 as sb
+    from sylver_b200 import gen
+    from oracle import ref
+    if not ref.available():
+        return None
+    n, ptr, row, val = gen.laplacian_27pt(grid)
+    order = gen.nested_dissection_order(grid)
+    s = sb.Solver()
+    inf = s.analyse(n, ptr, row, order)        # host-only symbolic analysis (shared input)
+    sym = s.symbolic()
+    ot = ref.OracleTree(sym)
+    for _ in range(max(0, warmup)):
+        ot.factor(val, True)
+    t = 0.0
+    for _ in range(steps):
+        t += ot.factor(val, True)
+    assert ot.stats.flag == 0
+    gf = steps * inf.num_flops / t / 1e9
+    sample = (f"27-point Laplacian {grid}^3 (n={n}, {inf.num_flops:.3e} flops/step), posdef, "
+              f"SSIDS CPU engine (task-sequential, OpenBLAS {cores} threads), {steps} steps in {t:.2f} s")
+    ot.close()
+    return dict(value=gf, cores=cores, sample=sample, seconds=t, flops=inf.num_flops)
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_reference_sample(a.sample_grid, a.steps, min(a.warmup, 1))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle.so missing (build needs /root/reference)"}))
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "lap27_100 (bounded CPU sample: lap27_%d)" % a.sample_grid,
+                   "note": "reference CPU path = SPRAL/SSIDS CPU engine built from /root/reference "
+                           "(full SyLVER/StarPU build is not producible: no Fortran, StarPU, hwloc, METIS)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def ours(a):
+    import numpy as np
+    import torch
+    import sylver_b200 as sb
+    from sylver_b200 import gen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the factorization path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = sb.lib()
+    sb.require_gpu()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- workload (synthetic), analysis excluded from timing ----
+    n, ptr, row, val = gen.laplacian_27pt(a.grid)
+    order = gen.nested_dissection_order(a.grid)
+    stream = torch.cuda.Stream()
+    L.sylver_b200_set_stream.argtypes = [C.c_void_p, C.c_int]
+    L.sylver_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
+    s = sb.Solver(ngpu=1)
+    t0 = time.perf_counter()
+    inf = s.analyse(n, ptr, row, order)
+    t_analyse = time.perf_counter() - t0
+    assert inf.flag == 0, inf.flag
+    num_flops = int(inf.num_flops)
+    d_val = torch.from_numpy(val).to("cuda")
+    h_val = torch.from_numpy(val).pin_memory()
+    dptr = int(d_val.data_ptr())
+    hval_np = h_val.numpy()
+
+    with torch.cuda.stream(stream):
+        # ---- value: inputs resident in HBM ----
+        for _ in range(a.warmup):
+            inf = s.factorize(dptr, posdef=True)
+            assert inf.flag == 0, inf.flag
+        launches_per_step = s.timings()["launches"]
+        clocks = ClockSampler(local)
+        barrier(); torch.cuda.synchronize()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            inf = s.factorize(dptr, posdef=True)
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        clk = clocks.stop()
+        dt = e0.elapsed_time(e1) * 1e-3
+        assert inf.flag == 0, inf.flag
+
+        # ---- e2e: host values through the public C API, H2D + flag D2H every step ----
+        for _ in range(min(a.warmup, 2)):
+            s.factorize(hval_np, posdef=True)
+        barrier(); torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        f0.record(stream)
+        for _ in range(a.steps):
+            inf = s.factorize(hval_np, posdef=True)
+            assert inf.flag == 0
+        f1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        dt_e2e = max(f0.elapsed_time(f1) * 1e-3, time.perf_counter() - w0)
+
+    # parity gate on the very factors that were timed (backward error, oracle-free property)
+    x0 = np.ones(n)
+    b = gen.sym_matvec(n, ptr, row, val, x0)
+    x = s.solve(b)
+    bwderr = gen.backward_error(n, ptr, row, val, x, b)
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel: profiled (un-graphed) pass with CUDA events ----
+    roof = None
+    breakdown = None
+    if rank == 0:
+        s.free()
+        os.environ["SYLVER_B200_PROFILE"] = "1"
+        sp = sb.Solver(ngpu=1)
+        sp.analyse(n, ptr, row, order)
+        with torch.cuda.stream(stream):
+            sp.factorize(dptr, posdef=True)
+            sp.factorize(dptr, posdef=True)
+            torch.cuda.synchronize()
+        prof = (C.c_double * 32)()
+        L.sylver_b200_numeric_tree_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        nk = L.sylver_b200_numeric_tree_profile(L.sylver_b200_fkeep_tree(sp.fkeep), prof, 32)
+        os.environ.pop("SYLVER_B200_PROFILE")
+        ms = {KNAMES[i]: prof[3 * i] for i in range(nk)}
+        nl = {KNAMES[i]: int(prof[3 * i + 1]) for i in range(nk)}
+        fl = {KNAMES[i]: prof[3 * i + 2] for i in range(nk)}
+        tot_ms = sum(ms.values())
+        g_ms = ms["trsm"] + ms["update"] + ms["contrib"]
+        g_fl = fl["trsm"] + fl["update"] + fl["contrib"]
+        g_nl = nl["trsm"] + nl["update"] + nl["contrib"]
+        peak = L.sylver_b200_bench_dmma(0, 0, 0, 5)
+        achieved = g_fl / (g_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_gemm_batched_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "kernel": "k_gemm_batched (DMMA.8x8x4 tiles: trsm+update+contrib)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "FP64 DMMA issue peak measured in this run by sylver_b200_bench_dmma(0) "
+                               "(MEASURED_PEAKS.json has no FP64 figure)",
+                "flops_per_launch": g_fl / max(g_nl, 1), "avg_launch_ms": g_ms / max(g_nl, 1),
+                "launches": g_nl, "share_of_step": g_ms / tot_ms, "traffic": traffic}
+        breakdown = {k: {"ms": round(ms[k], 3), "launches": nl[k]} for k in ms}
+        sp.free()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = run_reference_sample(a.sample_grid, 2, 1)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                   "sample": r["sample"]}
+
+    if rank == 0:
+        value = world * a.steps * num_flops / dt / 1e9
+        e2e = world * a.steps * num_flops / dt_e2e / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"lap27_{a.grid}", "n": n, "nnz_lower": int(ptr[-1] - 1),
+                       "num_flops": num_flops, "order": "geometric nested dissection (input)",
+                       "nemin": 32, "parallelism": "1 GPU" if world == 1 else f"replicas x{world}",
+                       "l2": "factor+contribution arenas (>20 GB) far exceed the 126 MB L2; no flush needed",
+                       "analyse_s": t_analyse, "bwderr": bwderr},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(val.nbytes),
+                    "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * dt_e2e / a.steps},
+            "gpu_launches": int(launches_per_step) * a.steps,
+            "clocks": clk,
+            "roofline": roof,
+            "kernel_breakdown_ms": breakdown,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -367,6 +367,18 @@ int sylver_b200_numeric_tree_timings(void const* tree, double* out4) {
    return 0;
 }
 
+int sylver_b200_numeric_tree_profile(void const* tree, double* out, int cap) {
+   if (!tree) return -1;
+   return numeric_tree_profile(static_cast<const NumericTree*>(tree), out, cap);
+}
+
+long sylver_b200_numeric_tree_bytes(void const* tree, long* factor_bytes, long* contrib_bytes) {
+   if (!tree) return -1;
+   return numeric_tree_bytes(static_cast<const NumericTree*>(tree), factor_bytes, contrib_bytes);
+}
+
+void sylver_b200_set_stream(void* cuda_stream, int enable) { set_user_stream(cuda_stream, enable != 0); }
+
 int sylver_b200_numeric_tree_get_front(void const* tree, int node, int* m, int* n, double* l, double* contrib) {
    if (!tree) return -1;
    return numeric_tree_get_front(static_cast<const NumericTree*>(tree), node, m, n, l, contrib);

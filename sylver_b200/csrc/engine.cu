@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -254,6 +255,15 @@ struct LevelPlan {
    size_t contrib_prefix;
 };
 
+enum KClass { KC_SCATTER = 0, KC_ZERO, KC_ASSEMBLE, KC_POTRF, KC_TRSM, KC_UPDATE, KC_CONTRIB, KC_COUNT };
+
+static cudaStream_t g_user_stream = nullptr;
+static bool g_have_user_stream = false;
+void set_user_stream(void* s, bool enable) {
+   g_user_stream = (cudaStream_t)s;
+   g_have_user_stream = enable;
+}
+
 struct NumericTree {
    SymbolicTree* st = nullptr;
    bool posdef = true;
@@ -275,7 +285,14 @@ struct NumericTree {
    std::vector<LevelPlan> levels;
    DevTree T{};
    cudaStream_t stream = nullptr;
+   bool own_stream = true;
    cudaGraphExec_t graph = nullptr;
+   // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
+   bool profile = false;
+   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+   double prof_ms[KC_COUNT] = {0};
+   long prof_launches[KC_COUNT] = {0};
+   double prof_flops[KC_COUNT] = {0};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    long launches = 0;
    double t_device = 0, t_h2d = 0, t_wall = 0;
@@ -404,6 +421,21 @@ static void build_posdef_plan(NumericTree* nt) {
       prefix.push_back(acc);
       lp.contrib_tiles = acc;
    }
+   // algorithmic flops per kernel class (lower triangle only, multiply and add counted)
+   for (int c = 0; c < KC_COUNT; ++c) nt->prof_flops[c] = 0;
+   for (int f = 0; f < N; ++f) {
+      const double m = nt->m[f], n = nt->n[f];
+      for (int p0 = 0; p0 < nt->n[f]; p0 += nb) {
+         const double pw = std::min(nb, nt->n[f] - p0), p1 = p0 + pw;
+         nt->prof_flops[KC_POTRF] += pw * pw * pw / 3.0;
+         nt->prof_flops[KC_TRSM] += (m - p1) * pw * pw;
+         // sum_{c=p1}^{n-1} (m - c) lower-triangle entries, 2*pw flops each
+         const double cnt = (n - p1) * m - (n * (n - 1) - p1 * (p1 - 1)) / 2.0;
+         nt->prof_flops[KC_UPDATE] += 2.0 * pw * cnt;
+      }
+      const double k = m - n;
+      nt->prof_flops[KC_CONTRIB] += n * k * (k + 1);
+   }
    nt->W_doubles = wmax;
    nt->d_prefix = dev_upload(prefix);
    nt->d_asm_work = dev_upload(asmw);
@@ -422,6 +454,22 @@ static void upload_geometry(NumericTree* nt) {
 }
 
 // Issue the whole posdef factorization on nt->stream (captured into a graph).
+namespace {
+struct ProfScope {
+   NumericTree* nt; int cls; cudaEvent_t a = nullptr, b = nullptr;
+   ProfScope(NumericTree* nt_, int cls_) : nt(nt_), cls(cls_) {
+      if (!nt->profile) return;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, nt->stream);
+   }
+   ~ProfScope() {
+      if (!nt->profile) return;
+      cudaEventRecord(b, nt->stream);
+      nt->prof_events.push_back({cls, {a, b}});
+   }
+};
+}  // namespace
+
 static void issue_posdef(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    cudaStream_t s = nt->stream;
@@ -433,6 +481,7 @@ static void issue_posdef(NumericTree* nt) {
    CU_TRY(cudaMemsetAsync(nt->d_fail + 1, 0x7f, sizeof(int), s));
    if (st->nent > 0) {
       const int blocks = (int)std::min<long>((st->nent + 255) / 256, 148 * 16);
+      ProfScope ps(nt, KC_SCATTER);
       k_scatter_a<<<blocks, 256, 0, s>>>(T, st->nent, st->d_nlist, st->d_anode, st->d_nrow, st->d_ncol,
                                          nt->d_aval, nt->d_scaling, st->d_rlist, st->d_rptr);
       ++launches;
@@ -441,31 +490,41 @@ static void issue_posdef(NumericTree* nt) {
       const LevelPlan& lp = nt->levels[l];
       const int* d_fr = st->d_level_nodes + lp.first;
       if (lp.max_children > 0) {
-         k_zero_contrib<<<dim3(16, lp.count), 256, 0, s>>>(T, d_fr);
+         {
+            ProfScope ps(nt, KC_ZERO);
+            k_zero_contrib<<<dim3(16, lp.count), 256, 0, s>>>(T, d_fr);
+         }
          ++launches;
          for (auto& w : lp.asm_work) {
             if (w.second == 0) continue;
+            ProfScope ps(nt, KC_ASSEMBLE);
             k_assemble<<<w.second, 256, 0, s>>>(T, nt->d_asm_work + w.first);
             ++launches;
          }
       }
       for (size_t si = 0; si < lp.steps.size(); ++si) {
          const LevelStep& ls = lp.steps[si];
-         k_potrf_inv<<<ls.cnt, PF_THREADS, PF_SMEM_BYTES, s>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         {
+            ProfScope ps(nt, KC_POTRF);
+            k_potrf_inv<<<ls.cnt, PF_THREADS, PF_SMEM_BYTES, s>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         }
          ++launches;
          if (ls.trsm_tiles > 0) {
             TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
+            ProfScope ps(nt, KC_TRSM);
             k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld);
             ++launches;
          }
          if (ls.upd_tiles > 0) {
             TileBatch b{d_fr, nt->d_prefix + ls.upd_prefix, ls.cnt};
+            ProfScope ps(nt, KC_UPDATE);
             k_gemm_batched<<<ls.upd_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, (int)si, nb, nullptr, 0);
             ++launches;
          }
       }
       if (lp.contrib_tiles > 0) {
          TileBatch b{d_fr, nt->d_prefix + lp.contrib_prefix, lp.count};
+         ProfScope ps(nt, KC_CONTRIB);
          k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0);
          ++launches;
       }
@@ -505,7 +564,13 @@ static void load_values(NumericTree* nt, const double* aval, const double* scali
 
 static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
    CU_TRY(cudaEventRecord(nt->ev0, nt->stream));
-   CU_TRY(cudaGraphLaunch(nt->graph, nt->stream));
+   if (nt->profile) {
+      for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+      nt->prof_events.clear();
+      issue_posdef(nt);
+   } else {
+      CU_TRY(cudaGraphLaunch(nt->graph, nt->stream));
+   }
    CU_TRY(cudaEventRecord(nt->ev1, nt->stream));
    int fail[2] = {0, 0};
    CU_TRY(cudaMemcpyAsync(fail, nt->d_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, nt->stream));
@@ -513,6 +578,15 @@ static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
    float ms = 0;
    CU_TRY(cudaEventElapsedTime(&ms, nt->ev0, nt->ev1));
    nt->t_device = ms * 1e-3;
+   if (nt->profile) {
+      for (int c = 0; c < KC_COUNT; ++c) { nt->prof_ms[c] = 0; nt->prof_launches[c] = 0; }
+      for (auto& e : nt->prof_events) {
+         float t = 0;
+         cudaEventElapsedTime(&t, e.second.first, e.second.second);
+         nt->prof_ms[e.first] += t;
+         nt->prof_launches[e.first]++;
+      }
+   }
    *stats = sylver_inform_c{};
    int maxfront = 0;
    for (int f = 0; f < nt->st->nnodes; ++f) maxfront = std::max(maxfront, nt->m[f]);
@@ -533,7 +607,16 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       nt->posdef = posdef;
       nt->opt = *options;
       nt->nb = 128;
-      CU_TRY(cudaStreamCreateWithFlags(&nt->stream, cudaStreamNonBlocking));
+      if (g_have_user_stream) {
+         nt->stream = g_user_stream;
+         nt->own_stream = false;
+      } else {
+         CU_TRY(cudaStreamCreateWithFlags(&nt->stream, cudaStreamNonBlocking));
+      }
+      {
+         const char* pe = getenv("SYLVER_B200_PROFILE");
+         nt->profile = pe && pe[0] == '1';
+      }
       CU_TRY(cudaEventCreate(&nt->ev0));
       CU_TRY(cudaEventCreate(&nt->ev1));
       CU_TRY(cudaMalloc(&nt->d_fail, 4 * sizeof(int)));
@@ -547,12 +630,14 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       CU_TRY(cudaMalloc(&nt->d_W, nt->W_doubles * sizeof(double)));
       upload_geometry(nt);
       // capture the launch sequence once
-      cudaGraph_t g = nullptr;
-      CU_TRY(cudaStreamBeginCapture(nt->stream, cudaStreamCaptureModeThreadLocal));
-      issue_posdef(nt);
-      CU_TRY(cudaStreamEndCapture(nt->stream, &g));
-      CU_TRY(cudaGraphInstantiate(&nt->graph, g, 0));
-      CU_TRY(cudaGraphDestroy(g));
+      if (!nt->profile) {
+         cudaGraph_t g = nullptr;
+         CU_TRY(cudaStreamBeginCapture(nt->stream, cudaStreamCaptureModeThreadLocal));
+         issue_posdef(nt);
+         CU_TRY(cudaStreamEndCapture(nt->stream, &g));
+         CU_TRY(cudaGraphInstantiate(&nt->graph, g, 0));
+         CU_TRY(cudaGraphDestroy(g));
+      }
       load_values(nt, aval, scaling);
       run_posdef(nt, stats);
    } catch (CudaFailure& e) {
@@ -593,7 +678,8 @@ void numeric_tree_destroy(NumericTree* nt) {
    cudaFree(nt->d_child_ptr); cudaFree(nt->d_child_list);
    if (nt->ev0) cudaEventDestroy(nt->ev0);
    if (nt->ev1) cudaEventDestroy(nt->ev1);
-   if (nt->stream) cudaStreamDestroy(nt->stream);
+   if (nt->stream && nt->own_stream) cudaStreamDestroy(nt->stream);
+   for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
    delete nt;
 }
 
@@ -602,6 +688,23 @@ void numeric_tree_timings(const NumericTree* nt, double* out4) {
    out4[1] = nt->t_h2d;
    out4[2] = nt->t_wall;
    out4[3] = (double)nt->launches;
+}
+
+long numeric_tree_bytes(const NumericTree* nt, long* factor_bytes, long* contrib_bytes) {
+   if (factor_bytes) *factor_bytes = (long)(nt->L_doubles * sizeof(double));
+   if (contrib_bytes) *contrib_bytes = (long)(nt->C_doubles * sizeof(double));
+   return (long)((nt->L_doubles + nt->C_doubles + nt->W_doubles) * sizeof(double));
+}
+
+// out: KC_COUNT triples (ms, launches, algorithmic flops); returns KC_COUNT or 0 if not profiled
+int numeric_tree_profile(const NumericTree* nt, double* out, int cap) {
+   if (!nt->profile) return 0;
+   for (int c = 0; c < KC_COUNT && 3 * c + 2 < cap; ++c) {
+      out[3 * c] = nt->prof_ms[c];
+      out[3 * c + 1] = (double)nt->prof_launches[c];
+      out[3 * c + 2] = nt->prof_flops[c];
+   }
+   return KC_COUNT;
 }
 
 int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib) {

@@ -68,5 +68,8 @@ bool numeric_tree_posdef(const NumericTree* nt);
 int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib);
 
 int device_count();
+int numeric_tree_profile(const NumericTree* nt, double* out, int cap);
+void set_user_stream(void* stream, bool enable);
+long numeric_tree_bytes(const NumericTree* nt, long* factor_bytes, long* contrib_bytes);
 
 }  // namespace sylver_b200

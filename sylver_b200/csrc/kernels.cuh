@@ -100,10 +100,12 @@ constexpr int GT_BN = 128;             // tile cols
 constexpr int GT_KT = 16;              // k-columns per stage
 constexpr int GT_LDS = 132;            // padded smem row stride (132 mod 16 == 4: conflict free)
 constexpr int GT_STAGES = 4;
-constexpr int GT_CONSUMERS = 8;        // warps
+constexpr int GT_CONSUMERS = 16;       // warps, 4 (M) x 4 (N), 32 x 32 each: 4 per SM sub-partition
 constexpr int GT_THREADS = (GT_CONSUMERS + 1) * 32;
+constexpr int GT_LDC = 130;            // epilogue staging stride (130 mod 8 == 2: conflict free)
 constexpr size_t GT_STAGE_DOUBLES = 2 * GT_KT * GT_LDS;
 constexpr size_t GT_SMEM_BYTES = GT_STAGES * GT_STAGE_DOUBLES * sizeof(double) + 2 * GT_STAGES * sizeof(uint64_t);
+static_assert((size_t)GT_BN * GT_LDC <= GT_STAGES * GT_STAGE_DOUBLES, "epilogue tile must fit in the pipeline buffers");
 
 struct GemmTile {
    const double* A;   // first row of the A operand tile, k = 0 column
@@ -111,11 +113,21 @@ struct GemmTile {
    int lda, ldb;      // column strides (doubles)
    int arows, brows;  // valid rows (<=128) in each operand tile (rounded up to even inside)
    int K;             // depth
+   // destination tile (for the L2 prefetch issued by the producer warp): column c of the
+   // tile starts at dst + c*ldd; rows [0,128) -- only when prefetch is set
+   const double* dst;
+   int ldd;
+   bool prefetch;
+   int pf_c0, pf_c1;  // tile-relative column range worth prefetching
+   int pf_lines;      // 128 B lines per column
 };
 
-// Runs the pipeline; on return acc[i][j][0..1] holds the 32x64 warp tile:
-// rows wm*32 + i*8 + g, cols wn*64 + j*8 + 2t + {0,1}.  Producer warp returns with acc untouched.
-__device__ __forceinline__ void gemm_tile_mainloop(const GemmTile& t, double* smem, double (&acc)[4][8][2]) {
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMERS * 32) : "memory"); }
+
+// Runs the pipeline; on return (consumer warps) the 128 x 128 product tile is staged in
+// shared memory as Cs[c*GT_LDC + r] and the consumer warps are synchronised.  Returns false
+// for the producer warp (which has nothing left to do).
+__device__ __forceinline__ bool gemm_tile_mainloop(const GemmTile& t, double* smem) {
    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_DOUBLES);
    uint64_t* empty = full + GT_STAGES;
    const int warp = threadIdx.x >> 5;
@@ -159,16 +171,24 @@ __device__ __forceinline__ void gemm_tile_mainloop(const GemmTile& t, double* sm
             else if (!same)
                tma_bulk_g2s(Bs + kc * GT_LDS, t.B + (size_t)(k0 + kc) * t.ldb, bbytes, &full[s]);
          }
+         if (kb == min(nk, GT_STAGES) - 1 && t.prefetch) {
+            // pull the destination tile into L2 while the tensor cores work
+            for (int c = t.pf_c0 + lane; c < t.pf_c1; c += 32) {
+               const char* p = reinterpret_cast<const char*>(t.dst + (size_t)c * t.ldd);
+               for (int q = 0; q < t.pf_lines; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + q * 128));
+            }
+         }
       }
-      return;
+      return false;
    }
    // ===== consumer warps =====
    const int wm = warp & 3, wn = warp >> 2;
    const int g = lane >> 2, tq = lane & 3;
+   double acc[4][4][2];
 #pragma unroll
    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
    for (int kb = 0; kb < nk; ++kb) {
       const int s = kb % GT_STAGES;
       const uint32_t ph = (kb / GT_STAGES) & 1;
@@ -178,24 +198,37 @@ __device__ __forceinline__ void gemm_tile_mainloop(const GemmTile& t, double* sm
       const int kv = min(GT_KT, t.K - kb * GT_KT);
       const int kg = (kv + 3) >> 2;
       const double* ap = As + tq * GT_LDS + wm * 32 + g;
-      const double* bp = Bs + tq * GT_LDS + wn * 64 + g;
+      const double* bp = Bs + tq * GT_LDS + wn * 32 + g;
 #pragma unroll 1
       for (int k4 = 0; k4 < kg; ++k4) {
-         double a[4], b[8];
+         double a[4], b[4];
 #pragma unroll
          for (int i = 0; i < 4; ++i) a[i] = ap[i * 8];
 #pragma unroll
-         for (int j = 0; j < 8; ++j) b[j] = bp[j * 8];
+         for (int j = 0; j < 4; ++j) b[j] = bp[j * 8];
 #pragma unroll
          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
          ap += 4 * GT_LDS;
          bp += 4 * GT_LDS;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
    }
+   // every stage has been consumed by this warp; once all consumers are here the pipeline
+   // buffers are dead and can hold the output tile
+   consumer_bar();
+#pragma unroll
+   for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+         double* col = smem + (size_t)(wn * 32 + j * 8 + 2 * tq + h) * GT_LDC + wm * 32 + g;
+#pragma unroll
+         for (int i = 0; i < 4; ++i) col[i * 8] = acc[i][j][h];
+      }
+   consumer_bar();
+   return true;
 }
 
 // Work descriptor of one batched launch: the participating fronts and an
@@ -218,7 +251,7 @@ __device__ __forceinline__ int find_front(const TileBatch& b, int item) {
 // mode 0: trailing update inside the L panel after block column [p0, p0+pw):
 //         L[r][c] -= sum_k L[r][k] L[c][k],  c in [p0+pw, n), r in [c, m)
 // mode 1: contribution block:  C[r-n][c-n] = beta*C - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
-// mode 2: panel solve with the inverted diagonal block W (pw x pw, ld 128):
+// mode 2: panel solve with the inverted diagonal block W (pw x pw, ld wld):
 //         L[r][p0+c] = sum_k L[r][p0+k] W[c][k],  r in [p0+pw, m)
 // nb is the block-column width; `step` the block column index.
 static __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -235,6 +268,12 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
 
    GemmTile t;
    int i0, j0;          // absolute front row / column of the tile origin
+   // destination addressing: element (r, c) of the tile (absolute front indices) lives at
+   // dbase + c*ldd + r ; valid iff  r in [rlo(c), m)  and  c in [clo, chi)
+   double* dbase;
+   int ldd, clo, chi, rmin;
+   bool lower;          // additionally require r >= c
+   int op;              // 0: dst -= v   1: dst = -v   2: dst = v
    if (mode == 2) {
       // tile origin rounded down to an even row so the TMA source stays 16 B aligned
       i0 = ((p0 + pw) & ~1) + local * GT_BM;
@@ -246,6 +285,8 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       t.ldb = wld;
       t.brows = pw;
       t.K = pw;
+      dbase = Lf; ldd = ldl; clo = p0; chi = p0 + pw; rmin = p0 + pw; lower = false; op = 2;
+      t.prefetch = false;
    } else {
       const int base = (mode == 0) ? (p0 + pw) : (n & ~1);
       const int cend = (mode == 0) ? n : m;
@@ -263,60 +304,58 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       t.lda = t.ldb = ldl;
       t.arows = min(GT_BM, m - i0);
       t.brows = min(GT_BN, m - j0);
+      if (mode == 0) {
+         dbase = Lf; ldd = ldl; clo = p0 + pw; chi = n; rmin = 0; lower = true; op = 0;
+         t.prefetch = true;
+      } else {
+         const int ldc = T.ldc[f];
+         dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
+         op = (T.nchild[f] > 0) ? 0 : 1;     // children were extend-added before the factorization
+         t.prefetch = (op == 0);
+      }
    }
-   double acc[4][8][2];
-   gemm_tile_mainloop(t, smem, acc);
+   t.dst = dbase + (size_t)j0 * ldd + i0;
+   t.ldd = ldd;
+   t.pf_c0 = max(0, clo - j0);
+   t.pf_c1 = min(GT_BN, chi - j0);
+   t.pf_lines = (min(GT_BM, m - i0) * 8 + 127) / 128;
+   if (!gemm_tile_mainloop(t, smem)) return;
+
+   // ---- coalesced epilogue: warp w owns tile columns w*8 .. w*8+7, lanes stride the rows ----
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   if (warp == GT_CONSUMERS) return;
-   const int wm = warp & 3, wn = warp >> 2, g = lane >> 2, tq = lane & 3;
-   if (mode == 2) {
+   const bool interior = (i0 + GT_BM <= m) && (j0 >= clo) && (j0 + GT_BN <= chi) && (i0 >= j0 + GT_BN - 1 || !lower) &&
+                         (i0 >= rmin);
+#pragma unroll 1
+   for (int cq = 0; cq < 8; cq += 4) {
+      double v[4][4], d[4][4];
+      double* gp[4];
+      bool cok[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int u = 0; u < 4; ++u) {
+         const int ct = warp * 8 + cq + u;          // column inside the tile
+         const int c = j0 + ct;
+         cok[u] = interior || (c >= clo && c < chi);
+         gp[u] = dbase + (size_t)c * ldd + i0;
 #pragma unroll
-         for (int h = 0; h < 2; ++h) {
-            const int c = wn * 64 + j * 8 + 2 * tq + h;
-            if (c >= pw) continue;
-            double* col = Lf + (size_t)(p0 + c) * ldl;
+         for (int q = 0; q < 4; ++q) v[u][q] = smem[(size_t)ct * GT_LDC + lane + 32 * q];
+      }
+      if (op == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const int r = i0 + wm * 32 + i * 8 + g;
-               if (r < m && r >= p0 + pw) col[r] = acc[i][j][h];
+         for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+               const int r = i0 + lane + 32 * q;
+               const bool ok = interior || (cok[u] && r < m && r >= rmin && (!lower || r >= j0 + warp * 8 + cq + u));
+               d[u][q] = ok ? gp[u][lane + 32 * q] : 0.0;
             }
-         }
-      return;
-   }
-   if (mode == 0) {
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-         for (int h = 0; h < 2; ++h) {
-            const int c = j0 + wn * 64 + j * 8 + 2 * tq + h;
-            if (c >= n) continue;
-            double* col = Lf + (size_t)c * ldl;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const int r = i0 + wm * 32 + i * 8 + g;
-               if (r < m && r >= c) col[r] -= acc[i][j][h];
-            }
-         }
-      return;
-   }
-   {
-      double* Cf = T.C + T.coff[f];
-      const int ldc = T.ldc[f];
-      const bool accum = T.nchild[f] > 0;     // children were extend-added before the factorization
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-         for (int h = 0; h < 2; ++h) {
-            const int c = j0 + wn * 64 + j * 8 + 2 * tq + h;
-            if (c < n || c >= m) continue;
-            double* col = Cf + (size_t)(c - n) * ldc - n;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const int r = i0 + wm * 32 + i * 8 + g;
-               if (r < m && r >= c) col[r] = accum ? col[r] - acc[i][j][h] : -acc[i][j][h];
-            }
+         for (int q = 0; q < 4; ++q) {
+            const int r = i0 + lane + 32 * q;
+            const bool ok = interior || (cok[u] && r < m && r >= rmin && (!lower || r >= j0 + warp * 8 + cq + u));
+            if (ok) gp[u][lane + 32 * q] = (op == 0) ? d[u][q] - v[u][q] : (op == 1 ? -v[u][q] : v[u][q]);
          }
    }
 }
