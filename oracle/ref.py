@@ -172,6 +172,17 @@ class OracleTree:
             pass
 
 
+def aligned_zeros(shape, align: int = 64) -> np.ndarray:
+    """Fortran-ordered float64 zeros whose data pointer is `align`-byte aligned.  SSIDS picks
+    block_ldlt (aligned 32x32 tile) or ldlt_tpp_factor per block by pointer alignment
+    (spral/src/ssids/cpu/kernels/ldlt_app.cxx, Block::factor), so pivot sequences -- hence
+    num_two -- are only reproducible with a fixed alignment."""
+    cnt = int(np.prod(shape))
+    raw = np.zeros(cnt + align // 8, dtype=np.float64)
+    off = (-raw.ctypes.data % align) // 8
+    return raw[off:off + cnt].reshape(shape, order="F")
+
+
 def align_lda(m: int) -> int:
     return int(lib().oracle_align_lda(m))
 
@@ -181,10 +192,10 @@ def factor_front_posdef(a: np.ndarray, n: int, blksz: int = 256):
     Returns (L panel m x n, contrib (m-n)^2, info) -- info == -1 on success."""
     m = a.shape[0]
     lda = align_lda(m)
-    buf = np.zeros((lda, n), order="F")
+    buf = aligned_zeros((lda, n))
     buf[:m, :] = np.tril(a)[:, :n]
     k = m - n
-    contrib = np.zeros((max(k, 1), max(k, 1)), order="F")
+    contrib = aligned_zeros((max(k, 1), max(k, 1)))
     info = C.c_int(0)
     lib().oracle_factor_front_posdef(m, n, _p(buf), lda, _p(contrib), blksz, C.byref(info))
     return buf[:m, :].copy(), contrib[:k, :k].copy(), info.value
@@ -195,12 +206,12 @@ def factor_front_indef(a: np.ndarray, n: int, options: CpuFactorOptions | None =
     opt = options or default_options()
     m = a.shape[0]
     lda = align_lda(m)
-    buf = np.zeros((lda, n), order="F")
+    buf = aligned_zeros((lda, n))
     buf[:m, :] = np.tril(a)[:, :n]
     d = np.zeros(2 * n + 2)
     perm = np.arange(1, n + 1, dtype=np.int32)
     k = m - n
-    contrib = np.zeros((max(k, 1), max(k, 1)), order="F")
+    contrib = aligned_zeros((max(k, 1), max(k, 1)))
     # the contribution block must hold A22 (the reference front code receives it zeroed and
     # applies the Schur update with beta = 0; add A22 afterwards in the caller)
     stats = ThreadStats()

@@ -177,6 +177,7 @@ class Solver:
         self.options = default_options()
         self.inform = Inform()
         self.n = 0
+        self.ptr = self.row = None
 
     def analyse(self, n, ptr, row, order, val=None, check=False):
         self.n = n
@@ -213,7 +214,9 @@ class Solver:
         self.L.sylver_b200_symbolic_tree_cmap(tree, C.byref(cptr), C.byref(cm))
         nn = self.symbolic()["nnodes"]
         p = np.ctypeslib.as_array(cptr, (nn + 1,)).copy()
-        return p, np.ctypeslib.as_array(cm, (max(int(p[nn]), 1),)).copy()[:int(p[nn])]
+        if int(p[nn]) == 0:
+            return p, np.zeros(0, dtype=np.int32)
+        return p, np.ctypeslib.as_array(cm, (int(p[nn]),)).copy()
 
     def factorize(self, val, posdef: bool, scale=None):
         """val: numpy array (host) or an int device address."""
