@@ -230,11 +230,31 @@ int sylver_b200_akeep_view(void *akeep, sylver_b200_symbolic_view *view);
 int sylver_b200_symbolic_tree_cmap(void *symbolic_tree, long const **cptr,
                                    int const **cmap);
 
+/* The SymbolicTree (seam object) owned by an akeep; borrowed. */
+void *sylver_b200_akeep_tree(void *akeep);
+
 /* Timings of the last factorization on an fkeep/numeric tree (seconds):
  * out[0]=total device time (CUDA events), out[1]=H2D of aval, out[2]=host
  * wall time of the call, out[3]=kernel launches issued. */
 int sylver_b200_numeric_tree_timings(void const *tree, double *out4);
 void *sylver_b200_fkeep_tree(void *fkeep);
+
+/* Per-kernel-class device time of the last factorization when the environment variable
+ * SYLVER_B200_PROFILE=1 was set at tree creation (un-graphed issue, CUDA events around
+ * every launch): out receives triples (ms, launches, algorithmic flops) for the classes
+ * scatter, zero, assemble, potrf|pivot, trsm|tpp, update, contrib.  Returns the number of
+ * classes (0 when profiling is off). */
+int sylver_b200_numeric_tree_profile(void const *tree, double *out, int cap);
+/* Device bytes held by a numeric tree (total; factor and contribution arenas separately). */
+long sylver_b200_numeric_tree_bytes(void const *tree, long *factor_bytes, long *contrib_bytes);
+/* Issue all work of subsequently created numeric trees on the caller's CUDA stream
+ * (cudaStream_t passed as void*); enable = 0 restores private streams. */
+void sylver_b200_set_stream(void *cuda_stream, int enable);
+/* Copy one front back to the host (tests): L panel m x n (ld m) and contribution block
+ * (m-n)^2 (ld m-n); either may be NULL.  For indefinite trees _indef returns the number
+ * of eliminated columns, D^-1 (2n doubles) and the pivot permutation (n ints, 1-based). */
+int sylver_b200_numeric_tree_get_front(void const *tree, int node, int *m, int *n, double *l, double *contrib);
+int sylver_b200_numeric_tree_get_front_indef(void const *tree, int node, int *nelim, double *d, int *perm);
 
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).

@@ -77,7 +77,9 @@ EXPORTS = [
     "spldlt_tree_solve_bwd_posdef_dbl", "sylver_b200_device_count", "sylver_b200_version",
     "sylver_b200_akeep_view", "sylver_b200_symbolic_tree_cmap", "sylver_b200_numeric_tree_timings",
     "sylver_b200_fkeep_tree", "sylver_b200_factor_front_posdef", "sylver_b200_factor_front_indef",
-    "sylver_b200_bench_dmma", "sylver_b200_bench_copy",
+    "sylver_b200_bench_dmma", "sylver_b200_bench_copy", "sylver_b200_akeep_tree",
+    "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
+    "sylver_b200_numeric_tree_get_front", "sylver_b200_numeric_tree_get_front_indef",
 ]
 
 
@@ -133,6 +135,14 @@ def lib() -> C.CDLL:
     L.sylver_b200_numeric_tree_get_front.argtypes = [vp, C.c_int, ip, ip, vp, vp]
     L.sylver_b200_factor_front_posdef.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                                   C.POINTER(C.c_float)]
+    L.sylver_b200_factor_front_indef.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, vp,
+                                                 C.POINTER(OptionsC), C.POINTER(InformC),
+                                                 C.POINTER(C.c_float)]
+    L.sylver_b200_numeric_tree_get_front_indef.argtypes = [vp, C.c_int, ip, vp, vp]
+    L.sylver_b200_numeric_tree_profile.argtypes = [vp, dp, C.c_int]
+    L.sylver_b200_numeric_tree_bytes.restype = C.c_long
+    L.sylver_b200_numeric_tree_bytes.argtypes = [vp, lp, lp]
+    L.sylver_b200_set_stream.argtypes = [vp, C.c_int]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -163,6 +173,44 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)       # raw (device) address
     return a.ctypes.data_as(C.c_void_p)
+
+
+def default_options_c() -> OptionsC:
+    """sylver::options_c with SyLVER's defaults (src/sylver_datatypes_mod.F90:97-198)."""
+    o = OptionsC()
+    o.print_level = 0
+    o.action = True
+    o.small = 1e-20
+    o.u = 0.01
+    o.multiplier = 1.1
+    o.small_subtree_threshold = 4 * 10 ** 6
+    o.nb = 256
+    o.pivot_method = 2
+    o.failed_pivot_method = 1
+    o.cpu_topology = 1
+    return o
+
+
+def factor_front_indef(a: np.ndarray, n: int, options: OptionsC | None = None):
+    """APTP LDL^T of the first n columns of the dense symmetric front ``a`` (m x m) on the
+    GPU (reference harness shape: tests/testing_factor_node_indef.hxx:44-460).
+    Returns dict(nelim, L (m x n), d (2n), perm (n, 1-based), contrib ((m-n)^2), stats, ms)."""
+    require_gpu()
+    opt = options or default_options_c()
+    m = a.shape[0]
+    lda = m
+    buf = np.zeros((lda, n), order="F")
+    buf[:m, :] = np.tril(a)[:, :n]
+    d = np.zeros(2 * n + 2)
+    perm = np.arange(1, n + 1, dtype=np.int32)
+    k = m - n
+    contrib = np.zeros((max(k, 1), max(k, 1)), order="F")
+    stats = InformC()
+    ms = C.c_float(0)
+    nelim = lib().sylver_b200_factor_front_indef(m, n, _ptr(perm), _ptr(buf), lda, _ptr(d), _ptr(contrib),
+                                                 C.byref(opt), C.byref(stats), C.byref(ms))
+    return dict(nelim=nelim, L=buf, d=d[:2 * n].copy(), perm=perm, contrib=contrib[:k, :k].copy(),
+                stats=stats, ms=ms.value)
 
 
 class Solver:

@@ -201,7 +201,7 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
    sylver_options_c copt = options_to_c(options);
    sylver_inform_c stats{};
    const double* sc = fk->scaling.empty() ? nullptr : fk->scaling.data();
-   if (fk->tree && fk->akeep == ak && fk->posdef == posdef && posdef) {
+   if (fk->tree && fk->akeep == ak && fk->posdef == posdef) {
       numeric_tree_refactor(fk->tree, val, sc, &stats);
    } else {
       if (fk->tree) { numeric_tree_destroy(fk->tree); fk->tree = nullptr; }
@@ -382,6 +382,11 @@ void sylver_b200_set_stream(void* cuda_stream, int enable) { set_user_stream(cud
 int sylver_b200_numeric_tree_get_front(void const* tree, int node, int* m, int* n, double* l, double* contrib) {
    if (!tree) return -1;
    return numeric_tree_get_front(static_cast<const NumericTree*>(tree), node, m, n, l, contrib);
+}
+
+int sylver_b200_numeric_tree_get_front_indef(void const* tree, int node, int* nelim, double* d, int* perm) {
+   if (!tree) return -1;
+   return numeric_tree_get_front_indef(static_cast<const NumericTree*>(tree), node, nelim, d, perm);
 }
 
 }  // extern "C"

@@ -204,3 +204,45 @@ extern "C" int sylver_b200_factor_front_posdef(int m, int n, double* a, int lda,
    delete st;
    return ret;
 }
+
+// Indefinite single front (reference harness tests/testing_factor_node_indef.hxx:44-460 drives
+// factor_front_indef the same way): APTP on the n fully-summed columns of an m x m symmetric
+// front, TPP on what fails, the rest is reported as delayed (nelim < n).
+extern "C" int sylver_b200_factor_front_indef(int m, int n, int* perm, double* a, int lda, double* d, double* contrib,
+                                               sylver_options_c const* options, sylver_inform_c* stats,
+                                               float* ms_out) {
+   if (device_count() == 0) return SYLVER_ERROR_CUDA_UNKNOWN;
+   SymbolicTree* st = one_front_tree(m, n, lda);
+   if (!st) return SYLVER_ERROR_UNKNOWN;
+   sylver_inform_c local{};
+   if (!stats) stats = &local;
+   NumericTree* nt = numeric_tree_create(false, st, a, nullptr, options, stats);
+   int ret;
+   if (!nt) {
+      ret = stats->flag ? stats->flag : SYLVER_ERROR_UNKNOWN;
+   } else {
+      double t[4];
+      numeric_tree_timings(nt, t);
+      if (ms_out) *ms_out = (float)(t[0] * 1e3);
+      std::vector<double> l((size_t)m * n);
+      std::vector<int> idx(n);
+      int mm, nn, nelim = 0;
+      ret = 0;
+      if (numeric_tree_get_front(nt, 0, &mm, &nn, l.data(), contrib) != 0 ||
+          numeric_tree_get_front_indef(nt, 0, &nelim, d, idx.data()) != 0)
+         ret = SYLVER_ERROR_CUDA_UNKNOWN;
+      if (ret == 0) {
+         for (int c = 0; c < n; ++c)
+            for (int r = c; r < m; ++r) a[(size_t)c * lda + r] = l[(size_t)c * m + r];
+         if (perm) {
+            std::vector<int> in(perm, perm + n);
+            for (int i = 0; i < n; ++i) perm[i] = in[idx[i] - 1];
+         }
+         ret = (stats->flag < 0) ? stats->flag : nelim;
+      }
+      numeric_tree_destroy(nt);
+   }
+   symbolic_tree_forget(st);
+   delete st;
+   return ret;
+}

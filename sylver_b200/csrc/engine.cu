@@ -17,24 +17,10 @@
 #include <cstring>
 #include <map>
 
-#include "kernels.cuh"
+#include "engine_impl.hpp"
 #include "kernels_solve.cuh"
 
 namespace sylver_b200 {
-
-#define CU_TRY(expr)                                                                    \
-   do {                                                                                 \
-      cudaError_t e__ = (expr);                                                         \
-      if (e__ != cudaSuccess) {                                                         \
-         fprintf(stderr, "sylver_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName(e__), \
-                 __FILE__, __LINE__, #expr);                                            \
-         throw CudaFailure{(int)e__};                                                   \
-      }                                                                                 \
-   } while (0)
-
-struct CudaFailure {
-   int code;
-};
 
 int device_count() {
    int n = 0;
@@ -45,19 +31,13 @@ int device_count() {
    return n;
 }
 
-template <typename T>
-static T* dev_upload(const T* h, size_t count) {
-   T* d = nullptr;
-   CU_TRY(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
-   if (count) CU_TRY(cudaMemcpy(d, h, count * sizeof(T), cudaMemcpyHostToDevice));
-   return d;
-}
-template <typename T>
-static T* dev_upload(const std::vector<T>& v) {
-   return dev_upload(v.data(), v.size());
-}
 
-static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+static cudaStream_t g_user_stream = nullptr;
+static bool g_have_user_stream = false;
+void set_user_stream(void* s, bool enable) {
+   g_user_stream = (cudaStream_t)s;
+   g_have_user_stream = enable;
+}
 
 // ===========================================================================
 // SymbolicTree
@@ -66,7 +46,7 @@ SymbolicTree::~SymbolicTree() {
    if (!on_device) return;
    cudaFree(d_rlist); cudaFree(d_rptr); cudaFree(d_nlist); cudaFree(d_anode); cudaFree(d_nrow);
    cudaFree(d_ncol); cudaFree(d_parent); cudaFree(d_nchild); cudaFree(d_cmap); cudaFree(d_cmapoff);
-   cudaFree(d_level_nodes);
+   cudaFree(d_level_nodes); cudaFree(d_nptr);
 }
 
 // Host-only copies needed again at upload time
@@ -74,6 +54,7 @@ struct SymbolicExtra {
    std::vector<long> rptr1;   // 1-based rptr as given
    std::vector<long> nlist;   // (src,dest) pairs as given
    std::vector<int> anode;    // owning front of each entry
+   std::vector<long> nptr1;   // 1-based nptr as given
 };
 static std::map<const SymbolicTree*, SymbolicExtra>& extras() {
    static std::map<const SymbolicTree*, SymbolicExtra> m;
@@ -155,6 +136,7 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
    // A -> front map
    SymbolicExtra& ex = extras()[st];
    ex.rptr1.assign(rptr, rptr + nnodes + 1);
+   ex.nptr1.assign(nptr, nptr + nnodes + 1);
    st->nent = nnodes ? nptr[nnodes] - 1 : 0;
    ex.nlist.assign(nlist, nlist + 2 * st->nent);
    ex.anode.resize(st->nent);
@@ -172,6 +154,7 @@ static void symbolic_tree_upload(SymbolicTree* st) {
    st->d_rlist = dev_upload(st->rlist);
    st->d_rptr = dev_upload(ex.rptr1);
    st->d_nlist = dev_upload(ex.nlist);
+   st->d_nptr = dev_upload(ex.nptr1);
    st->d_anode = dev_upload(ex.anode);
    st->d_nrow = dev_upload(st->nrow);
    st->d_ncol = dev_upload(st->ncol);
@@ -187,158 +170,51 @@ static void symbolic_tree_upload(SymbolicTree* st) {
 
 void symbolic_tree_forget(const SymbolicTree* st) { extras().erase(st); }
 
-// ===========================================================================
-// Contribution arena planning (static: m - n never changes, even with delays)
-// ===========================================================================
-namespace {
-struct SegAlloc {
-   // first-fit free list over [0, inf), sizes in doubles
-   std::map<long, long> free_;   // offset -> size
-   long top = 0;
-   long peak = 0;
-   long alloc(long sz) {
-      for (auto it = free_.begin(); it != free_.end(); ++it) {
-         if (it->second >= sz) {
-            long off = it->first;
-            long rem = it->second - sz;
-            free_.erase(it);
-            if (rem > 0) free_[off + sz] = rem;
-            return off;
-         }
-      }
-      // extend the top (merge with a trailing free segment if adjacent)
-      long off = top;
-      if (!free_.empty()) {
-         auto last = std::prev(free_.end());
-         if (last->first + last->second == top) {
-            off = last->first;
-            free_.erase(last);
-         }
-      }
-      top = off + sz;
-      peak = std::max(peak, top);
-      return off;
-   }
-   void release(long off, long sz) {
-      auto it = free_.emplace(off, sz).first;
-      auto nx = std::next(it);
-      if (nx != free_.end() && it->first + it->second == nx->first) {
-         it->second += nx->second;
-         free_.erase(nx);
-      }
-      if (it != free_.begin()) {
-         auto pv = std::prev(it);
-         if (pv->first + pv->second == it->first) {
-            pv->second += it->second;
-            free_.erase(it);
-         }
-      }
-   }
-};
-}  // namespace
-
-// ===========================================================================
-// NumericTree
-// ===========================================================================
-struct LevelStep {
-   int cnt;             // fronts of the level that own block column `s`
-   int wld;             // stride of the inverse slots for this step
-   int trsm_tiles, upd_tiles;
-   size_t trsm_prefix, upd_prefix;   // offsets into d_prefix
-};
-struct LevelPlan {
-   int first, count;               // range in level_nodes
-   int max_children;
-   std::vector<std::pair<size_t, int>> asm_work;   // per child ordinal: (offset, count) in d_asm_work
-   std::vector<LevelStep> steps;
-   int contrib_tiles;
-   size_t contrib_prefix;
-};
-
-enum KClass { KC_SCATTER = 0, KC_ZERO, KC_ASSEMBLE, KC_POTRF, KC_TRSM, KC_UPDATE, KC_CONTRIB, KC_COUNT };
-
-static cudaStream_t g_user_stream = nullptr;
-static bool g_have_user_stream = false;
-void set_user_stream(void* s, bool enable) {
-   g_user_stream = (cudaStream_t)s;
-   g_have_user_stream = enable;
-}
-
-struct NumericTree {
-   SymbolicTree* st = nullptr;
-   bool posdef = true;
-   sylver_options_c opt{};
-   int nb = 128;
-   // per-front geometry (host) + device mirrors
-   std::vector<int> m, n, ldl, ldc;
-   std::vector<long> loff, coff;
-   int *d_m = nullptr, *d_n = nullptr, *d_ldl = nullptr, *d_ldc = nullptr;
-   long *d_loff = nullptr, *d_coff = nullptr;
-   double* d_L = nullptr; size_t L_doubles = 0;
-   double* d_C = nullptr; size_t C_doubles = 0;
-   double* d_W = nullptr; size_t W_doubles = 0;
-   double* d_aval = nullptr; size_t aval_count = 0;
-   double* d_scaling = nullptr;
-   int* d_fail = nullptr;
-   int* d_prefix = nullptr;
-   int2* d_asm_work = nullptr;
-   std::vector<LevelPlan> levels;
-   DevTree T{};
-   cudaStream_t stream = nullptr;
-   bool own_stream = true;
-   cudaGraphExec_t graph = nullptr;
-   // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
-   bool profile = false;
-   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
-   double prof_ms[KC_COUNT] = {0};
-   long prof_launches[KC_COUNT] = {0};
-   double prof_flops[KC_COUNT] = {0};
-   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-   long launches = 0;
-   double t_device = 0, t_h2d = 0, t_wall = 0;
-   // solve workspace
-   double* d_xw = nullptr;        // sum of m doubles
-   long* d_xwoff = nullptr;
-   std::vector<long> xwoff;
-   int* d_child_ptr = nullptr; int* d_child_list = nullptr;
-};
-
 bool numeric_tree_posdef(const NumericTree* nt) { return nt->posdef; }
 
-static void build_posdef_plan(NumericTree* nt) {
+// contribution arena: allocate a level's blocks, then release its children's.  Static even
+// with delayed pivots (m - n never changes).
+void plan_contrib_arena(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
-   const int nb = nt->nb;
-   nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N); nt->ldc.resize(N);
-   nt->loff.resize(N); nt->coff.assign(N, 0);
-   long loff = 0;
-   for (int f = 0; f < N; ++f) {
-      nt->m[f] = st->nrow[f];
-      nt->n[f] = st->ncol[f];
-      nt->ldl[f] = round_up(nt->m[f], 4);
-      nt->ldc[f] = round_up(std::max(nt->m[f] - nt->n[f], 1), 4);
-      nt->loff[f] = loff;
-      loff += (long)nt->ldl[f] * nt->n[f];
-   }
-   nt->L_doubles = loff + 4;
-   // contribution arena: allocate a level's blocks, then release its children's
+   nt->ldc.resize(N);
+   nt->coff.assign(N, 0);
+   for (int f = 0; f < N; ++f) nt->ldc[f] = round_up(std::max(st->nrow[f] - st->ncol[f], 1), 4);
    SegAlloc sa;
    for (int l = 0; l < st->nlevels; ++l) {
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
-         const long k = nt->m[f] - nt->n[f];
+         const long k = st->nrow[f] - st->ncol[f];
          if (k > 0) nt->coff[f] = sa.alloc((long)nt->ldc[f] * k);
       }
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
          for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
             const int c = st->child_list[ci];
-            const long k = nt->m[c] - nt->n[c];
+            const long k = st->nrow[c] - st->ncol[c];
             if (k > 0) sa.release(nt->coff[c], (long)nt->ldc[c] * k);
          }
       }
    }
    nt->C_doubles = sa.peak + 4;
+}
+
+static void build_posdef_plan(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes;
+   const int nb = nt->nb;
+   nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N);
+   nt->loff.resize(N);
+   long loff = 0;
+   for (int f = 0; f < N; ++f) {
+      nt->m[f] = st->nrow[f];
+      nt->n[f] = st->ncol[f];
+      nt->ldl[f] = round_up(nt->m[f], 4);
+      nt->loff[f] = loff;
+      loff += (long)nt->ldl[f] * nt->n[f];
+   }
+   nt->L_doubles = loff + 4;
+   plan_contrib_arena(nt);
 
    // work lists
    std::vector<int> prefix;
@@ -441,7 +317,7 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->d_asm_work = dev_upload(asmw);
 }
 
-static void upload_geometry(NumericTree* nt) {
+void upload_geometry(NumericTree* nt) {
    nt->d_m = dev_upload(nt->m); nt->d_n = dev_upload(nt->n);
    nt->d_ldl = dev_upload(nt->ldl); nt->d_ldc = dev_upload(nt->ldc);
    nt->d_loff = dev_upload(nt->loff); nt->d_coff = dev_upload(nt->coff);
@@ -452,23 +328,6 @@ static void upload_geometry(NumericTree* nt) {
    T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
    T.L = nt->d_L; T.C = nt->d_C;
 }
-
-// Issue the whole posdef factorization on nt->stream (captured into a graph).
-namespace {
-struct ProfScope {
-   NumericTree* nt; int cls; cudaEvent_t a = nullptr, b = nullptr;
-   ProfScope(NumericTree* nt_, int cls_) : nt(nt_), cls(cls_) {
-      if (!nt->profile) return;
-      cudaEventCreate(&a); cudaEventCreate(&b);
-      cudaEventRecord(a, nt->stream);
-   }
-   ~ProfScope() {
-      if (!nt->profile) return;
-      cudaEventRecord(b, nt->stream);
-      nt->prof_events.push_back({cls, {a, b}});
-   }
-};
-}  // namespace
 
 static void issue_posdef(NumericTree* nt) {
    SymbolicTree* st = nt->st;
@@ -541,7 +400,7 @@ static void set_kernel_attributes() {
    done = true;
 }
 
-static void load_values(NumericTree* nt, const double* aval, const double* scaling) {
+void load_values(NumericTree* nt, const double* aval, const double* scaling) {
    SymbolicTree* st = nt->st;
    // number of values referenced = max src index; the caller's array covers ptr[n]-1 entries,
    // which equals nent for a full-rank analysis.  Copy exactly what the map references.
@@ -623,7 +482,13 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       // values: the map references entries 1..max(src)
       nt->aval_count = (size_t)st->nval;
       CU_TRY(cudaMalloc(&nt->d_aval, std::max<size_t>(nt->aval_count, 1) * sizeof(double)));
-      if (!posdef) throw CudaFailure{-98};   // indefinite path is issued by engine_indef.cu
+      if (!posdef) {
+         indef_setup(nt);
+         load_values(nt, aval, scaling);
+         run_indef(nt, stats);
+         nt->t_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+         return nt;
+      }
       build_posdef_plan(nt);
       CU_TRY(cudaMalloc(&nt->d_L, nt->L_doubles * sizeof(double)));
       CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
@@ -660,7 +525,8 @@ void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* sc
    auto w0 = std::chrono::steady_clock::now();
    try {
       load_values(nt, aval, scaling);
-      run_posdef(nt, stats);
+      if (nt->posdef) run_posdef(nt, stats);
+      else run_indef(nt, stats);
    } catch (CudaFailure&) {
       *stats = sylver_inform_c{};
       stats->flag = SYLVER_ERROR_CUDA_UNKNOWN;
@@ -671,6 +537,7 @@ void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* sc
 void numeric_tree_destroy(NumericTree* nt) {
    if (!nt) return;
    if (nt->graph) cudaGraphExecDestroy(nt->graph);
+   indef_destroy(nt);
    cudaFree(nt->d_m); cudaFree(nt->d_n); cudaFree(nt->d_ldl); cudaFree(nt->d_ldc);
    cudaFree(nt->d_loff); cudaFree(nt->d_coff); cudaFree(nt->d_L); cudaFree(nt->d_C);
    cudaFree(nt->d_W); cudaFree(nt->d_aval); cudaFree(nt->d_scaling); cudaFree(nt->d_fail);
@@ -707,6 +574,19 @@ int numeric_tree_profile(const NumericTree* nt, double* out, int cap) {
    return KC_COUNT;
 }
 
+int numeric_tree_get_front_indef(const NumericTree* nt, int node, int* nelim, double* d, int* perm) {
+   if (node < 0 || node >= nt->st->nnodes || nt->posdef) return -1;
+   const int nn = nt->n[node];
+   if (nelim) *nelim = nt->nelim[node];
+   try {
+      if (d) CU_TRY(cudaMemcpy(d, nt->T.D + nt->doff[node], 2 * (size_t)nn * sizeof(double), cudaMemcpyDeviceToHost));
+      if (perm) CU_TRY(cudaMemcpy(perm, nt->T.perm + nt->permoff[node], (size_t)nn * sizeof(int), cudaMemcpyDeviceToHost));
+   } catch (CudaFailure&) {
+      return -51;
+   }
+   return 0;
+}
+
 int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib) {
    if (node < 0 || node >= nt->st->nnodes) return -1;
    const int mm = nt->m[node], nn = nt->n[node];
@@ -714,7 +594,7 @@ int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, doub
    if (n) *n = nn;
    try {
       if (l)
-         CU_TRY(cudaMemcpy2D(l, (size_t)mm * sizeof(double), nt->d_L + nt->loff[node],
+         CU_TRY(cudaMemcpy2D(l, (size_t)mm * sizeof(double), nt->T.L + nt->loff[node],
                              (size_t)nt->ldl[node] * sizeof(double), (size_t)mm * sizeof(double), nn,
                              cudaMemcpyDeviceToHost));
       const int k = mm - nn;
@@ -773,7 +653,13 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
       a.child_ptr = nt->d_child_ptr;
       a.child_list = nt->d_child_list;
       a.posdef = nt->posdef ? 1 : 0;
+      if (!nt->posdef) {
+         a.perm = nt->T.perm; a.permoff = nt->d_permoff;
+         a.D = nt->T.D; a.doff = nt->d_doff;
+         a.nelim = nt->d_nelim;
+      }
       const bool do_fwd = (job == 0 || job == 1);
+      const bool do_diag = !nt->posdef && (job == 0 || job == 2 || job == 4);
       const bool do_bwd = (job == 0 || job == 3 || job == 4);
       for (int r = 0; r < nrhs; ++r) {
          a.x = dx + (size_t)r * ldx;
@@ -782,6 +668,7 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
                const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;
                k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, st->d_level_nodes + first);
             }
+         if (do_diag) k_solve_diag<<<(st->nnodes + 7) / 8, 256, 0, nt->stream>>>(a, st->nnodes);
          if (do_bwd)
             for (int l = st->nlevels - 1; l >= 0; --l) {
                const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;

@@ -38,6 +38,7 @@ struct SymbolicTree {
    int* d_cmap = nullptr;
    long* d_cmapoff = nullptr;
    int* d_level_nodes = nullptr;
+   long* d_nptr = nullptr;       // 1-based values as given (nnodes+1)
    bool on_device = false;
    int device = 0;
 
@@ -66,6 +67,9 @@ bool numeric_tree_posdef(const NumericTree* nt);
 // Debug / test access: copy one front's L panel (m x n, ld m) and contribution
 // ((m-n)^2, ld m-n) to host buffers (either may be null). Returns 0 or <0.
 int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, double* l, double* contrib);
+
+// indefinite fronts: eliminated column count, D^-1 (2n doubles) and the pivot permutation (n ints)
+int numeric_tree_get_front_indef(const NumericTree* nt, int node, int* nelim, double* d, int* perm);
 
 int device_count();
 int numeric_tree_profile(const NumericTree* nt, double* out, int cap);

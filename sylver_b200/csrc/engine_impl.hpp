@@ -1,0 +1,200 @@
+// Private definitions shared by engine.cu (plan, posdef path, solves) and
+// engine_indef.cu (APTP path).
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "engine.hpp"
+#include "kernels.cuh"
+
+namespace sylver_b200 {
+
+#define CU_TRY(expr)                                                                    \
+   do {                                                                                 \
+      cudaError_t e__ = (expr);                                                         \
+      if (e__ != cudaSuccess) {                                                         \
+         fprintf(stderr, "sylver_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName(e__), \
+                 __FILE__, __LINE__, #expr);                                            \
+         throw CudaFailure{(int)e__};                                                   \
+      }                                                                                 \
+   } while (0)
+
+struct CudaFailure {
+   int code;
+};
+
+template <typename T>
+static T* dev_upload(const T* h, size_t count) {
+   T* d = nullptr;
+   CU_TRY(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+   if (count) CU_TRY(cudaMemcpy(d, h, count * sizeof(T), cudaMemcpyHostToDevice));
+   return d;
+}
+template <typename T>
+static T* dev_upload(const std::vector<T>& v) {
+   return dev_upload(v.data(), v.size());
+}
+
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// ===========================================================================
+// Contribution arena planning (static: m - n never changes, even with delays)
+// ===========================================================================
+namespace {
+struct SegAlloc {
+   // first-fit free list over [0, inf), sizes in doubles
+   std::map<long, long> free_;   // offset -> size
+   long top = 0;
+   long peak = 0;
+   long alloc(long sz) {
+      for (auto it = free_.begin(); it != free_.end(); ++it) {
+         if (it->second >= sz) {
+            long off = it->first;
+            long rem = it->second - sz;
+            free_.erase(it);
+            if (rem > 0) free_[off + sz] = rem;
+            return off;
+         }
+      }
+      // extend the top (merge with a trailing free segment if adjacent)
+      long off = top;
+      if (!free_.empty()) {
+         auto last = std::prev(free_.end());
+         if (last->first + last->second == top) {
+            off = last->first;
+            free_.erase(last);
+         }
+      }
+      top = off + sz;
+      peak = std::max(peak, top);
+      return off;
+   }
+   void release(long off, long sz) {
+      auto it = free_.emplace(off, sz).first;
+      auto nx = std::next(it);
+      if (nx != free_.end() && it->first + it->second == nx->first) {
+         it->second += nx->second;
+         free_.erase(nx);
+      }
+      if (it != free_.begin()) {
+         auto pv = std::prev(it);
+         if (pv->first + pv->second == it->first) {
+            pv->second += it->second;
+            free_.erase(it);
+         }
+      }
+   }
+};
+}  // namespace
+
+// ===========================================================================
+// NumericTree
+// ===========================================================================
+struct LevelStep {
+   int cnt;             // fronts of the level that own block column `s`
+   int wld;             // stride of the inverse slots for this step
+   int trsm_tiles, upd_tiles;
+   size_t trsm_prefix, upd_prefix;   // offsets into d_prefix
+};
+struct LevelPlan {
+   int first, count;               // range in level_nodes
+   int max_children;
+   std::vector<std::pair<size_t, int>> asm_work;   // per child ordinal: (offset, count) in d_asm_work
+   std::vector<LevelStep> steps;
+   int contrib_tiles;
+   size_t contrib_prefix;
+};
+
+enum KClass { KC_SCATTER = 0, KC_ZERO, KC_ASSEMBLE, KC_POTRF, KC_TRSM, KC_UPDATE, KC_CONTRIB, KC_COUNT };
+
+
+struct NumericTree {
+   SymbolicTree* st = nullptr;
+   bool posdef = true;
+   sylver_options_c opt{};
+   int nb = 128;
+   // per-front geometry (host) + device mirrors
+   std::vector<int> m, n, ldl, ldc;
+   std::vector<long> loff, coff;
+   int *d_m = nullptr, *d_n = nullptr, *d_ldl = nullptr, *d_ldc = nullptr;
+   long *d_loff = nullptr, *d_coff = nullptr;
+   double* d_L = nullptr; size_t L_doubles = 0;
+   double* d_C = nullptr; size_t C_doubles = 0;
+   double* d_W = nullptr; size_t W_doubles = 0;
+   double* d_aval = nullptr; size_t aval_count = 0;
+   double* d_scaling = nullptr;
+   int* d_fail = nullptr;
+   int* d_prefix = nullptr;
+   int2* d_asm_work = nullptr;
+   std::vector<LevelPlan> levels;
+   DevTree T{};
+   cudaStream_t stream = nullptr;
+   bool own_stream = true;
+   cudaGraphExec_t graph = nullptr;
+   // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
+   bool profile = false;
+   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+   double prof_ms[KC_COUNT] = {0};
+   long prof_launches[KC_COUNT] = {0};
+   double prof_flops[KC_COUNT] = {0};
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   long launches = 0;
+   double t_device = 0, t_h2d = 0, t_wall = 0;
+   // solve workspace
+   double* d_xw = nullptr;        // sum of m doubles
+   long* d_xwoff = nullptr;
+   std::vector<long> xwoff;
+   int* d_child_ptr = nullptr; int* d_child_list = nullptr;
+   // ---- indefinite (APTP) path: dynamic geometry, see engine_indef.cu ----
+   struct Chunk { double* ptr; size_t cap, used; };
+   std::vector<Chunk> chunks;            // factor arena: L panel + D^-1 + perm per front, bump allocated
+   std::vector<int> nelim;               // host copy, per front (valid after its level completed)
+   std::vector<long> woff, doff, permoff;
+   int* d_ncol0 = nullptr;
+   long *d_woff = nullptr, *d_doff = nullptr, *d_permoff = nullptr;
+   FrontState* d_state = nullptr;
+   int* d_nelim = nullptr;               // per front (device), for the solves
+   int* d_stats = nullptr;               // 8 ints, see k_front_stats
+   void* d_diag = nullptr;               // DiagScratch per front of the widest level
+   size_t diag_cap = 0;
+   void* d_lvl = nullptr;                // per-level upload buffer (geometry updates, orders, prefixes)
+   void* h_lvl = nullptr;                // pinned mirror
+   size_t lvl_cap = 0;
+   int* d_lvl_out = nullptr;             // nelim of the level's fronts (read back per level)
+   int* h_lvl_out = nullptr;
+   size_t lvl_out_cap = 0;
+   size_t Wscratch_cap = 0;
+   int num_delay = 0, maxfront = 0;
+};
+
+namespace {
+struct ProfScope {
+   NumericTree* nt; int cls; cudaEvent_t a = nullptr, b = nullptr;
+   ProfScope(NumericTree* nt_, int cls_) : nt(nt_), cls(cls_) {
+      if (!nt->profile) return;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, nt->stream);
+   }
+   ~ProfScope() {
+      if (!nt->profile) return;
+      cudaEventRecord(b, nt->stream);
+      nt->prof_events.push_back({cls, {a, b}});
+   }
+};
+}  // namespace
+
+
+// engine_indef.cu
+void run_indef(NumericTree* nt, sylver_inform_c* stats);
+void indef_setup(NumericTree* nt);
+void indef_destroy(NumericTree* nt);
+void plan_contrib_arena(NumericTree* nt);
+void upload_geometry(NumericTree* nt);
+void load_values(NumericTree* nt, const double* aval, const double* scaling);
+
+}  // namespace sylver_b200

@@ -1,0 +1,380 @@
+// Indefinite (APTP) numeric factorization: host-side level scheduler.
+//
+// Replaces NumericTree::factor_mf_indef + the StarPU task graph of
+// FactorIndefAPP (reference src/NumericTree.hxx:186-406, src/factor_indef.hxx:1484-1646,
+// src/factor_failed.hxx:28-157, src/assemble.hxx:152-302).
+//
+// Delayed pivots change the size of the parent front at run time
+// (reference NumericFront.hxx:79-95), so unlike the positive definite path the launch
+// sequence is not pre-captured: levels of the assembly tree are issued one after the
+// other; after each level the host reads back one int per front (its eliminated column
+// count), sizes the parents (m, n, ldl, arena offsets) and uploads one packed buffer with
+// the next level's geometry and work lists.  Everything inside a level -- block sizes,
+// pass counts, failed-column swaps, update extents -- is decided on the device from the
+// per-front FrontState; the host never looks at numerical values.
+#include "engine_impl.hpp"
+#include "kernels_indef.cuh"
+
+namespace sylver_b200 {
+
+struct GeoUpd {
+   int f, m, n, ldl;
+   long loff, woff, doff, permoff;
+};
+
+static __global__ void k_set_geometry(const GeoUpd* __restrict__ u, int cnt, int* m, int* n, int* ldl, long* loff,
+                                      long* woff, long* doff, long* permoff) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= cnt) return;
+   const GeoUpd g = u[i];
+   m[g.f] = g.m; n[g.f] = g.n; ldl[g.f] = g.ldl;
+   loff[g.f] = g.loff; woff[g.f] = g.woff; doff[g.f] = g.doff; permoff[g.f] = g.permoff;
+}
+
+static __global__ void k_copy_nelim(const int* __restrict__ fronts, const int* __restrict__ lvl_nelim, int cnt,
+                                    int* __restrict__ nelim_all) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < cnt) nelim_all[fronts[i]] = lvl_nelim[i];
+}
+
+// ---- factor arena: bump allocation in chunks, offsets relative to chunk 0 ----
+static long arena_alloc(NumericTree* nt, size_t doubles) {
+   doubles = (doubles + 15) & ~(size_t)15;
+   for (;;) {
+      NumericTree::Chunk& c = nt->chunks.back();
+      if (c.used + doubles <= c.cap) {
+         const long off = (long)((c.ptr + c.used) - nt->chunks[0].ptr);
+         c.used += doubles;
+         return off;
+      }
+      // grow: a new chunk (only reached when delays outgrow the analyse-time estimate)
+      NumericTree::Chunk nc{nullptr, std::max<size_t>(doubles, std::max<size_t>(nt->chunks[0].cap / 4, (size_t)1 << 24)), 0};
+      CU_TRY(cudaMalloc(&nc.ptr, nc.cap * sizeof(double)));
+      nt->chunks.push_back(nc);
+   }
+}
+
+template <typename T>
+static void ensure_cap(T*& dptr, size_t& cap, size_t need) {
+   if (need <= cap) return;
+   if (dptr) CU_TRY(cudaFree(dptr));
+   cap = need + need / 4 + 64;
+   CU_TRY(cudaMalloc(&dptr, cap * sizeof(T)));
+}
+
+void indef_setup(NumericTree* nt) {
+   // kernels.cuh kernels are per translation unit (static __global__): this TU's copy needs its
+   // own opt-in to > 48 KB of dynamic shared memory
+   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes;
+   nt->m.assign(N, 0); nt->n.assign(N, 0); nt->ldl.assign(N, 0); nt->loff.assign(N, 0);
+   nt->woff.assign(N, 0); nt->doff.assign(N, 0); nt->permoff.assign(N, 0);
+   nt->nelim.assign(N, 0);
+   plan_contrib_arena(nt);
+   CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
+   size_t est = 0;
+   for (int f = 0; f < N; ++f) {
+      const size_t ldl = round_up(st->nrow[f], 4);
+      est += ((ldl * st->ncol[f] + 2 * (size_t)st->ncol[f] + (st->ncol[f] + 1) / 2 + 15) & ~(size_t)15);
+   }
+   est += est / 50 + ((size_t)1 << 16);
+   NumericTree::Chunk c0{nullptr, est, 0};
+   CU_TRY(cudaMalloc(&c0.ptr, c0.cap * sizeof(double)));
+   nt->chunks.push_back(c0);
+   nt->L_doubles = est;
+   CU_TRY(cudaMalloc(&nt->d_m, N * sizeof(int)));
+   CU_TRY(cudaMalloc(&nt->d_n, N * sizeof(int)));
+   CU_TRY(cudaMalloc(&nt->d_ldl, N * sizeof(int)));
+   CU_TRY(cudaMalloc(&nt->d_loff, N * sizeof(long)));
+   CU_TRY(cudaMalloc(&nt->d_woff, N * sizeof(long)));
+   CU_TRY(cudaMalloc(&nt->d_doff, N * sizeof(long)));
+   CU_TRY(cudaMalloc(&nt->d_permoff, N * sizeof(long)));
+   CU_TRY(cudaMalloc(&nt->d_state, N * sizeof(FrontState)));
+   CU_TRY(cudaMalloc(&nt->d_nelim, N * sizeof(int)));
+   CU_TRY(cudaMalloc(&nt->d_stats, 8 * sizeof(int)));
+   nt->d_ldc = dev_upload(nt->ldc);
+   nt->d_coff = dev_upload(nt->coff);
+   nt->d_ncol0 = dev_upload(st->ncol);
+   DevTree& T = nt->T;
+   T.m = nt->d_m; T.n = nt->d_n; T.ldl = nt->d_ldl; T.ldc = nt->d_ldc;
+   T.loff = nt->d_loff; T.coff = nt->d_coff; T.cmapoff = st->d_cmapoff;
+   T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
+   T.L = nt->chunks[0].ptr; T.C = nt->d_C;
+   T.ncol0 = nt->d_ncol0; T.woff = nt->d_woff; T.doff = nt->d_doff; T.permoff = nt->d_permoff;
+   T.W = nullptr; T.D = nt->chunks[0].ptr; T.perm = reinterpret_cast<int*>(nt->chunks[0].ptr);
+   T.state = nt->d_state;
+   for (int c = 0; c < KC_COUNT; ++c) nt->prof_flops[c] = 0;
+}
+
+void indef_destroy(NumericTree* nt) {
+   for (size_t i = 0; i < nt->chunks.size(); ++i) cudaFree(nt->chunks[i].ptr);
+   nt->chunks.clear();
+   cudaFree(nt->d_ncol0); cudaFree(nt->d_woff); cudaFree(nt->d_doff); cudaFree(nt->d_permoff);
+   cudaFree(nt->d_state); cudaFree(nt->d_nelim); cudaFree(nt->d_stats); cudaFree(nt->d_diag);
+   cudaFree(nt->d_lvl); cudaFree(nt->d_lvl_out);
+   if (nt->h_lvl) cudaFreeHost(nt->h_lvl);
+   if (nt->h_lvl_out) cudaFreeHost(nt->h_lvl_out);
+   nt->d_ncol0 = nullptr; nt->d_woff = nt->d_doff = nt->d_permoff = nullptr;
+   nt->d_state = nullptr; nt->d_nelim = nt->d_stats = nullptr; nt->d_diag = nullptr;
+   nt->d_lvl = nullptr; nt->h_lvl = nullptr; nt->d_lvl_out = nullptr; nt->h_lvl_out = nullptr;
+}
+
+namespace {
+// packs heterogeneous arrays into one upload buffer, 16 B aligned sections
+struct Packer {
+   std::vector<char> buf;
+   template <typename T>
+   size_t put(const std::vector<T>& v) {
+      const size_t off = (buf.size() + 15) & ~(size_t)15;
+      buf.resize(off + v.size() * sizeof(T));
+      if (!v.empty()) memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
+      return off;
+   }
+};
+}  // namespace
+
+void run_indef(NumericTree* nt, sylver_inform_c* stats) {
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes;
+   cudaStream_t s = nt->stream;
+   const double u = nt->opt.u, small = nt->opt.small;
+   const bool tpp_everywhere = (nt->opt.failed_pivot_method != 2) || (nt->opt.pivot_method == 3);
+   long launches = 0;
+   for (auto& c : nt->chunks) c.used = 0;
+   if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
+   if (nt->profile) {
+      for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+      nt->prof_events.clear();
+   }
+   CU_TRY(cudaEventRecord(nt->ev0, s));
+   CU_TRY(cudaMemsetAsync(nt->d_stats, 0, 8 * sizeof(int), s));
+   int maxfront = 0;
+   std::vector<int> order;
+   for (int l = 0; l < st->nlevels; ++l) {
+      const int first = st->level_ptr[l], cnt = st->level_ptr[l + 1] - first;
+      if (cnt == 0) continue;
+      // ---- geometry of the level (children are complete: their nelim is known) ----
+      order.assign(st->level_nodes.begin() + first, st->level_nodes.begin() + first + cnt);
+      std::vector<GeoUpd> geo(cnt);
+      std::vector<int2> delay_work;
+      size_t wtotal = 0;
+      std::vector<std::pair<size_t, size_t>> runs;      // arena ranges to clear (bytes offsets from chunk 0)
+      int max_children = 0, maxn = 0;
+      for (int i = 0; i < cnt; ++i) {
+         const int f = order[i];
+         int nd = 0;
+         for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
+            const int c = st->child_list[ci];
+            const int d = nt->n[c] - nt->nelim[c];
+            if (d > 0) delay_work.push_back(make_int2(c, st->ncol[f] + nd));
+            nd += d;
+         }
+         max_children = std::max(max_children, st->nchild[f]);
+         const int m = st->nrow[f] + nd, n = st->ncol[f] + nd;
+         const int ldl = round_up(m, 4);
+         nt->m[f] = m; nt->n[f] = n; nt->ldl[f] = ldl;
+         maxn = std::max(maxn, n);
+         maxfront = std::max(maxfront, m);
+         const size_t panel = (size_t)ldl * n;
+         const size_t block = panel + 2 * (size_t)n + (n + 1) / 2;
+         const long off = arena_alloc(nt, block);
+         nt->loff[f] = off;
+         nt->doff[f] = off + (long)panel;
+         nt->permoff[f] = 2 * (off + (long)panel + 2 * (long)n);
+         nt->woff[f] = (long)wtotal;
+         wtotal += (panel + 15) & ~(size_t)15;
+         const size_t bytes = ((block + 15) & ~(size_t)15) * sizeof(double);
+         if (!runs.empty() && runs.back().first + runs.back().second == (size_t)off * sizeof(double))
+            runs.back().second += bytes;
+         else
+            runs.emplace_back((size_t)off * sizeof(double), bytes);
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nt->n[a] > nt->n[b]; });
+      for (int i = 0; i < cnt; ++i) {
+         const int f = order[i];
+         geo[i] = GeoUpd{f, nt->m[f], nt->n[f], nt->ldl[f], nt->loff[f], nt->woff[f], nt->doff[f], nt->permoff[f]};
+      }
+      // work lists (prefix sums are nested: step s uses the first cnt_s fronts of `order`)
+      std::vector<int> row_prefix(cnt + 1), upd_prefix(cnt + 1), con_prefix(cnt + 1);
+      {
+         int a0 = 0, a1 = 0, a2 = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = order[i];
+            const int m = nt->m[f], n = nt->n[f];
+            row_prefix[i] = a0; upd_prefix[i] = a1; con_prefix[i] = a2;
+            a0 += 1 + (m + AP_THREADS - 1) / AP_THREADS;
+            const int TR = (m + GT_BM - 1) / GT_BM, TC = (n + GT_BN - 1) / GT_BN;
+            for (int tj = 0; tj < TC; ++tj) a1 += TR - tj;
+            if (m > n) {
+               const int base = n & ~1;
+               const int TRc = (m - base + GT_BM - 1) / GT_BM;
+               a2 += TRc * (TRc + 1) / 2;
+            }
+         }
+         row_prefix[cnt] = a0; upd_prefix[cnt] = a1; con_prefix[cnt] = a2;
+      }
+      std::vector<int2> asmw;
+      std::vector<std::pair<size_t, int>> asm_ranges;
+      for (int q = 0; q < max_children; ++q) {
+         const size_t off = asmw.size();
+         for (int i = 0; i < cnt; ++i) {
+            const int f = order[i];
+            if (st->nchild[f] <= q) continue;
+            const int c = st->child_list[st->child_ptr[f] + q];
+            const int k = st->nrow[c] - st->ncol[c];
+            for (int j0 = 0; j0 < k; j0 += 32) asmw.push_back(make_int2(c, j0));
+         }
+         asm_ranges.emplace_back(off, (int)(asmw.size() - off));
+      }
+      Packer pk;
+      const size_t o_geo = pk.put(geo), o_order = pk.put(order), o_row = pk.put(row_prefix),
+                   o_upd = pk.put(upd_prefix), o_con = pk.put(con_prefix), o_asm = pk.put(asmw),
+                   o_del = pk.put(delay_work);
+      // ---- device buffers for the level ----
+      {
+         char* dl = static_cast<char*>(nt->d_lvl);
+         if (pk.buf.size() > nt->lvl_cap) {
+            CU_TRY(cudaStreamSynchronize(s));
+            if (nt->h_lvl) CU_TRY(cudaFreeHost(nt->h_lvl));
+            size_t cap = nt->lvl_cap;
+            ensure_cap(dl, cap, pk.buf.size());
+            nt->d_lvl = dl;
+            nt->lvl_cap = cap;
+            CU_TRY(cudaMallocHost(&nt->h_lvl, cap));
+         }
+         if ((size_t)cnt > nt->lvl_out_cap) {
+            CU_TRY(cudaStreamSynchronize(s));
+            if (nt->h_lvl_out) CU_TRY(cudaFreeHost(nt->h_lvl_out));
+            ensure_cap(nt->d_lvl_out, nt->lvl_out_cap, (size_t)cnt);
+            CU_TRY(cudaMallocHost(&nt->h_lvl_out, nt->lvl_out_cap * sizeof(int)));
+         }
+         if ((size_t)cnt > nt->diag_cap) {
+            CU_TRY(cudaStreamSynchronize(s));
+            DiagScratch* dd = static_cast<DiagScratch*>(nt->d_diag);
+            ensure_cap(dd, nt->diag_cap, (size_t)cnt);
+            nt->d_diag = dd;
+         }
+         if (wtotal > nt->Wscratch_cap) {
+            CU_TRY(cudaStreamSynchronize(s));
+            ensure_cap(nt->d_W, nt->Wscratch_cap, wtotal);
+            nt->W_doubles = nt->Wscratch_cap;
+         }
+      }
+      nt->T.W = nt->d_W;
+      const DevTree& T = nt->T;
+      memcpy(nt->h_lvl, pk.buf.data(), pk.buf.size());
+      CU_TRY(cudaMemcpyAsync(nt->d_lvl, nt->h_lvl, pk.buf.size(), cudaMemcpyHostToDevice, s));
+      char* dl = static_cast<char*>(nt->d_lvl);
+      const GeoUpd* d_geo = reinterpret_cast<const GeoUpd*>(dl + o_geo);
+      const int* d_fr = reinterpret_cast<const int*>(dl + o_order);
+      const int* d_row = reinterpret_cast<const int*>(dl + o_row);
+      const int* d_upd = reinterpret_cast<const int*>(dl + o_upd);
+      const int* d_con = reinterpret_cast<const int*>(dl + o_con);
+      const int2* d_asm = reinterpret_cast<const int2*>(dl + o_asm);
+      const int2* d_del = reinterpret_cast<const int2*>(dl + o_del);
+      DiagScratch* d_diag = static_cast<DiagScratch*>(nt->d_diag);
+      k_set_geometry<<<(cnt + 255) / 256, 256, 0, s>>>(d_geo, cnt, nt->d_m, nt->d_n, nt->d_ldl, nt->d_loff, nt->d_woff,
+                                                       nt->d_doff, nt->d_permoff);
+      for (auto& r : runs)
+         CU_TRY(cudaMemsetAsync(reinterpret_cast<char*>(nt->chunks[0].ptr) + r.first, 0, r.second, s));
+      launches += 1 + (long)runs.size();
+      // ---- assembly: A entries, children's generated elements, delayed columns ----
+      {
+         ProfScope ps(nt, KC_SCATTER);
+         k_init_front<<<cnt, 256, 0, s>>>(T, d_fr, st->d_rlist, st->d_rptr);
+         k_scatter_a_fronts<<<cnt, 256, 0, s>>>(T, d_fr, st->d_nptr, st->d_nlist, st->d_nrow, nt->d_aval, nt->d_scaling,
+                                                st->d_rlist, st->d_rptr);
+         launches += 2;
+      }
+      if (max_children > 0) {
+         {
+            ProfScope ps(nt, KC_ZERO);
+            k_zero_contrib<<<dim3(16, cnt), 256, 0, s>>>(T, d_fr);
+            ++launches;
+         }
+         ProfScope ps(nt, KC_ASSEMBLE);
+         for (auto& w : asm_ranges) {
+            if (w.second == 0) continue;
+            k_assemble_indef<<<w.second, 256, 0, s>>>(T, d_asm + w.first);
+            ++launches;
+         }
+         if (!delay_work.empty()) {
+            k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
+            ++launches;
+         }
+      }
+      // ---- APTP block columns ----
+      const int nsteps = (maxn + IB - 1) / IB;
+      int cnt_s = cnt;
+      for (int sidx = 0; sidx < nsteps; ++sidx) {
+         while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= sidx * IB) --cnt_s;
+         if (cnt_s == 0) break;
+         TileBatch rb{d_fr, d_row, cnt_s};
+         TileBatch ub{d_fr, d_upd, cnt_s};
+         {
+            ProfScope ps(nt, KC_POTRF);
+            k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
+            k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
+            k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
+            k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
+            launches += 4;
+         }
+         {
+            ProfScope ps(nt, KC_UPDATE);
+            k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0);
+            ++launches;
+         }
+      }
+      // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
+      {
+         ProfScope ps(nt, KC_TRSM);
+         k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
+         ++launches;
+      }
+      if (con_prefix[cnt] > 0) {
+         TileBatch cb{d_fr, d_con, cnt};
+         ProfScope ps(nt, KC_CONTRIB);
+         k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0);
+         ++launches;
+      }
+      k_front_stats<<<(cnt + 127) / 128, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out);
+      k_copy_nelim<<<(cnt + 255) / 256, 256, 0, s>>>(d_fr, nt->d_lvl_out, cnt, nt->d_nelim);
+      launches += 2;
+      CU_TRY(cudaMemcpyAsync(nt->h_lvl_out, nt->d_lvl_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      CU_TRY(cudaGetLastError());
+      for (int i = 0; i < cnt; ++i) nt->nelim[order[i]] = nt->h_lvl_out[i];
+   }
+   CU_TRY(cudaEventRecord(nt->ev1, s));
+   int hs[8];
+   CU_TRY(cudaMemcpyAsync(hs, nt->d_stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+   CU_TRY(cudaStreamSynchronize(s));
+   float ms = 0;
+   CU_TRY(cudaEventElapsedTime(&ms, nt->ev0, nt->ev1));
+   nt->t_device = ms * 1e-3;
+   nt->launches = launches;
+   if (nt->profile) {
+      for (int c = 0; c < KC_COUNT; ++c) { nt->prof_ms[c] = 0; nt->prof_launches[c] = 0; }
+      for (auto& e : nt->prof_events) {
+         float t = 0;
+         cudaEventElapsedTime(&t, e.second.first, e.second.second);
+         nt->prof_ms[e.first] += t;
+         nt->prof_launches[e.first]++;
+      }
+   }
+   *stats = sylver_inform_c{};
+   stats->num_delay = hs[0];
+   stats->num_neg = hs[1];
+   stats->num_two = hs[2];
+   stats->num_zero = hs[3];
+   stats->not_first_pass = hs[4];
+   stats->not_second_pass = hs[5];
+   stats->maxfront = maxfront;
+   // roots cannot delay: what TPP leaves at a root are exact zero columns (counted above when
+   // they were eliminated as zero pivots) -- anything else means a singular matrix and !action
+   if (!nt->opt.action && hs[3] > 0) stats->flag = SYLVER_ERROR_SINGULAR;
+   (void)N;
+}
+
+}  // namespace sylver_b200

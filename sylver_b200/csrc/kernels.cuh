@@ -16,6 +16,18 @@
 
 namespace sylver_b200 {
 
+// Progress of the APTP factorization of one front (indefinite path only).
+struct FrontState {
+   int p0;       // columns eliminated so far: the contiguous prefix [0, p0)
+   int na;       // end of the active candidates; [na, n) failed their block and wait for TPP
+   int npass;    // columns of the current block that pass the a-posteriori test (atomicMin)
+   int kbeg;     // pivots the next trailing update applies: [kbeg, kbeg + klen)
+   int klen;
+   int wb;       // width of the current block
+   int nelim1;   // eliminated by the first (APTP) pass
+   int nelim;    // eliminated in total; n - nelim columns are delayed to the parent
+};
+
 // Device view of the assembly tree (structure-of-arrays, one entry per front).
 struct DevTree {
    const int* m;         // rows of the front (nrow + ndelay_in)
@@ -30,6 +42,15 @@ struct DevTree {
    const int* cmap;      // concatenated child->parent row maps (0-based)
    double* L;            // factor arena
    double* C;            // contribution arena
+   // ---- indefinite path only ----
+   const int* ncol0;     // fully-summed columns before delays (n - ncol0 = ndelay_in)
+   const long* woff;     // offset of the front's W = L*D scratch panel (same shape as L)
+   const long* doff;     // offset of D^-1 (2 doubles per column)
+   const long* permoff;  // offset of the front's pivot permutation (n ints, 1-based variables)
+   double* W;
+   double* D;
+   int* perm;
+   FrontState* state;
 };
 
 // ---------------------------------------------------------------------------
@@ -274,7 +295,42 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    int ldd, clo, chi, rmin;
    bool lower;          // additionally require r >= c
    int op;              // 0: dst -= v   1: dst = -v   2: dst = v
-   if (mode == 2) {
+   if (mode >= 3) {
+      // ---- indefinite path: operands are W = L*D (A side) and L (B side); the extent of the
+      // update is read from the device-resident front state (nothing here is known to the host)
+      const FrontState st = T.state[f];
+      const double* Wf = T.W + T.woff[f];
+      const int kbeg = (mode == 3) ? st.kbeg : 0;
+      t.K = (mode == 3) ? st.klen : st.nelim;
+      if (mode == 3 && t.K == 0) return;
+      const int first = (mode == 3) ? st.p0 : n;     // first column/row of the updated region
+      const int base = first & ~1;
+      const int cend = (mode == 3) ? n : m;
+      if (cend <= first) return;
+      const int TR = (m - base + GT_BM - 1) / GT_BM;
+      const int TC = (cend - base + GT_BN - 1) / GT_BN;
+      int tj = 0;
+      while (tj < TC && local >= TR - tj) { local -= TR - tj; ++tj; }
+      if (tj >= TC) return;
+      const int ti = tj + local;
+      i0 = base + ti * GT_BM;
+      j0 = base + tj * GT_BN;
+      t.A = Wf + (size_t)kbeg * ldl + i0;
+      t.B = Lf + (size_t)kbeg * ldl + j0;
+      t.lda = t.ldb = ldl;
+      t.arows = min(GT_BM, m - i0);
+      t.brows = min(GT_BN, m - j0);
+      if (mode == 3) {
+         dbase = Lf; ldd = ldl; clo = first; chi = n; rmin = 0; lower = true; op = 0;
+         t.prefetch = true;
+      } else {
+         const int ldc = T.ldc[f];
+         dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
+         op = (T.nchild[f] > 0) ? 0 : 1;
+         if (op == 0 && t.K == 0) return;
+         t.prefetch = (op == 0);
+      }
+   } else if (mode == 2) {
       // tile origin rounded down to an even row so the TMA source stays 16 B aligned
       i0 = ((p0 + pw) & ~1) + local * GT_BM;
       j0 = p0;

@@ -41,7 +41,13 @@ static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_fwd(SolveArgs a,
    double* xw = a.xw + a.xwoff[f];
    const int* rl = a.rlist + (a.rptr[f] - 1);
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   for (int i = tid; i < m; i += SOLVE_THREADS) xw[i] = (i < n) ? a.x[var_index(a, f, i, rl)] : 0.0;
+   // Children's updates arrive in the front's ORIGINAL row order (cmap); pivoting permuted the
+   // fully-summed rows, so they are first summed in original order, folded into the global
+   // vector at the front's own variables (rl[j], exclusively ours), and only then gathered in
+   // pivot order.  Rows >= n are untouched by pivoting (shifted by the delays).
+   const int ncol0 = (int)(a.rptr[f + 1] - a.rptr[f]) - (m - n);
+   const int nd = n - ncol0;
+   for (int i = tid; i < m; i += SOLVE_THREADS) xw[i] = 0.0;
    __syncthreads();
    for (int ci = a.child_ptr[f]; ci < a.child_ptr[f + 1]; ++ci) {
       const int c = a.child_list[ci];
@@ -49,9 +55,16 @@ static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_fwd(SolveArgs a,
       const int k = a.T.m[c] - cn;
       const int* cm = a.T.cmap + a.T.cmapoff[c];
       const double* src = a.xw + a.xwoff[c];
-      for (int i = tid; i < k; i += SOLVE_THREADS) xw[cm[i]] += src[cn + i];
+      for (int i = tid; i < k; i += SOLVE_THREADS) {
+         const int r = cm[i];
+         xw[r < ncol0 ? r : r + nd] += src[cn + i];
+      }
       __syncthreads();
    }
+   for (int j = tid; j < ncol0; j += SOLVE_THREADS) a.x[rl[j] - 1] += xw[j];
+   __syncthreads();
+   for (int i = tid; i < n; i += SOLVE_THREADS) xw[i] = a.x[var_index(a, f, i, rl)];
+   __syncthreads();
    for (int j0 = 0; j0 < ne; j0 += 32) {
       const int jb = min(32, ne - j0);
       if (warp == 0) {
@@ -115,6 +128,30 @@ static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_bwd(SolveArgs a,
       __syncthreads();
    }
    for (int i = tid; i < ne; i += SOLVE_THREADS) a.x[var_index(a, f, i, rl)] = xw[i];
+}
+
+// D^-1 application of every front (indefinite only; ldlt_app_solve_diag,
+// spral/src/ssids/cpu/kernels/ldlt_app.cxx:2556-2578).  One warp per front.
+static __global__ void __launch_bounds__(256) k_solve_diag(SolveArgs a, int nfronts) {
+   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (f >= nfronts) return;
+   const int lane = threadIdx.x & 31;
+   const int ne = a.nelim[f];
+   const double* d = a.D + a.doff[f];
+   const int* perm = a.perm + a.permoff[f];
+   double* xw = a.xw + a.xwoff[f];
+   for (int i = lane; i < ne; i += 32) {
+      const bool second = (i > 0) && isinf(d[2 * i]);
+      const bool first = (i + 1 < ne) && isinf(d[2 * i + 2]);
+      const double xi = a.x[perm[i] - 1];
+      double r;
+      if (second) r = d[2 * i - 1] * a.x[perm[i - 1] - 1] + d[2 * i + 1] * xi;
+      else if (first) r = d[2 * i] * xi + d[2 * i + 1] * a.x[perm[i + 1] - 1];
+      else r = d[2 * i] * xi;
+      xw[i] = r;          // staged: 2x2 partners may be handled by another pass of the loop
+   }
+   __syncwarp();
+   for (int i = lane; i < ne; i += 32) a.x[perm[i] - 1] = xw[i];
 }
 
 }  // namespace sylver_b200
