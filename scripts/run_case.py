@@ -18,15 +18,42 @@ from sylver_b200 import gen
 KNAMES = ["scatter", "zero", "assemble", "potrf", "trsm", "update", "contrib"]
 
 
+def dense(a):
+    """config 2: single dense front m x ncol, random symmetric indefinite (glibc rand, seed 1)."""
+    m, n = a.k, (a.ncol or a.k // 4)
+    rng = gen.GlibcRand(1)
+    A = gen.dense_sym_indef(m, rng=rng)
+    if a.delays:
+        A = gen.cause_delays(A, rng)
+    flops = sum((m - n + j) ** 2 for j in range(1, n + 1))
+    for r in range(a.reps):
+        res = sb.factor_front_indef(A, n)
+        st = res["stats"]
+        print(json.dumps(dict(rep=r, m=m, n=n, nelim=res["nelim"], ms=res["ms"], gflops=flops / (res["ms"] * 1e-3) / 1e9,
+                              num_neg=st.num_neg, num_two=st.num_two, num_delay=st.num_delay,
+                              not_first_pass=st.not_first_pass, not_second_pass=st.not_second_pass)), flush=True)
+    if a.oracle:
+        from oracle import ref
+        t = time.time()
+        ro = ref.factor_front_indef(A, n)
+        t = time.time() - t
+        print(json.dumps(dict(oracle_s=t, oracle_gflops=flops / t / 1e9, nelim=int(ro["nelim"]),
+                              num_neg=ro["stats"].num_neg, num_two=ro["stats"].num_two)))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("kind", choices=["lap7", "lap27", "kkt"])
+    ap.add_argument("kind", choices=["lap7", "lap27", "kkt", "dense"])
     ap.add_argument("k", type=int)
+    ap.add_argument("--ncol", type=int, default=0, help="dense: fully-summed columns (default m/4)")
+    ap.add_argument("--delays", action="store_true", help="dense: apply cause_delays")
     ap.add_argument("--indef", action="store_true")
     ap.add_argument("--oracle", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--nosolve", action="store_true")
     a = ap.parse_args()
+    if a.kind == "dense":
+        return dense(a)
     t0 = time.time()
     if a.kind == "lap7":
         n, ptr, row, val = gen.laplacian_7pt(a.k)

@@ -142,6 +142,8 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
    ex.anode.resize(st->nent);
    for (int i = 0; i < nnodes; ++i)
       for (long e = nptr[i] - 1; e < nptr[i + 1] - 1; ++e) ex.anode[e] = i;
+   st->aent.resize(nnodes);
+   for (int i = 0; i < nnodes; ++i) st->aent[i] = nptr[i + 1] - nptr[i];
    st->nval = 0;
    for (long e = 0; e < st->nent; ++e) st->nval = std::max(st->nval, nlist[2 * e]);
    return st;
@@ -230,6 +232,7 @@ static void build_posdef_plan(NumericTree* nt) {
       int maxn = 0;
       for (int i = 0; i < lp.count; ++i) {
          lp.max_children = std::max(lp.max_children, st->nchild[fr[i]]);
+         if (st->nchild[fr[i]] > 0) lp.max_contrib = std::max(lp.max_contrib, nt->m[fr[i]] - nt->n[fr[i]]);
          maxn = std::max(maxn, nt->n[fr[i]]);
       }
       // assembly: q-th child of every parent of this level
@@ -351,7 +354,7 @@ static void issue_posdef(NumericTree* nt) {
       if (lp.max_children > 0) {
          {
             ProfScope ps(nt, KC_ZERO);
-            k_zero_contrib<<<dim3(16, lp.count), 256, 0, s>>>(T, d_fr);
+            k_zero_contrib<<<dim3(zero_grid_x(lp.max_contrib), lp.count), 256, 0, s>>>(T, d_fr);
          }
          ++launches;
          for (auto& w : lp.asm_work) {

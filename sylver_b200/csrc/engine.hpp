@@ -21,6 +21,7 @@ struct SymbolicTree {
    std::vector<int> nrow, ncol, parent, nchild, level;
    std::vector<int> child_ptr, child_list;   // children in decreasing index order (reference order)
    std::vector<long> rptr;                   // 0-based offsets into rlist
+   std::vector<long> aent;                   // entries of A mapped into each front
    std::vector<int> rlist;                   // 1-based row indices (as given)
    std::vector<long> cmapoff;                // per node, offset into cmap
    std::vector<int> cmap;                    // child contribution row -> parent local row (0-based)

@@ -41,6 +41,11 @@ static T* dev_upload(const std::vector<T>& v) {
 }
 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+// CTAs per front for k_zero_contrib: enough to saturate HBM on the widest block of the level
+static inline int zero_grid_x(int maxk) {
+   const long bytes = (long)maxk * maxk * 8;
+   return (int)std::min<long>(std::max<long>(bytes / (256 * 16 * 8), 1), 1184);
+}
 
 // ===========================================================================
 // Contribution arena planning (static: m - n never changes, even with delays)
@@ -104,6 +109,7 @@ struct LevelStep {
 struct LevelPlan {
    int first, count;               // range in level_nodes
    int max_children;
+   int max_contrib = 0;            // largest contribution block order among fronts with children
    std::vector<std::pair<size_t, int>> asm_work;   // per child ordinal: (offset, count) in d_asm_work
    std::vector<LevelStep> steps;
    int contrib_tiles;

@@ -160,7 +160,8 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       std::vector<int2> delay_work;
       size_t wtotal = 0;
       std::vector<std::pair<size_t, size_t>> runs;      // arena ranges to clear (bytes offsets from chunk 0)
-      int max_children = 0, maxn = 0;
+      int max_children = 0, maxn = 0, maxk = 0;
+      long max_ent = 0;
       for (int i = 0; i < cnt; ++i) {
          const int f = order[i];
          int nd = 0;
@@ -171,6 +172,8 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
             nd += d;
          }
          max_children = std::max(max_children, st->nchild[f]);
+         if (st->nchild[f] > 0) maxk = std::max(maxk, st->nrow[f] - st->ncol[f]);
+         max_ent = std::max(max_ent, st->aent[f]);
          const int m = st->nrow[f] + nd, n = st->ncol[f] + nd;
          const int ldl = round_up(m, 4);
          nt->m[f] = m; nt->n[f] = n; nt->ldl[f] = ldl;
@@ -283,14 +286,15 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       {
          ProfScope ps(nt, KC_SCATTER);
          k_init_front<<<cnt, 256, 0, s>>>(T, d_fr, st->d_rlist, st->d_rptr);
-         k_scatter_a_fronts<<<cnt, 256, 0, s>>>(T, d_fr, st->d_nptr, st->d_nlist, st->d_nrow, nt->d_aval, nt->d_scaling,
+         const int gy = (int)std::min<long>(std::max<long>((max_ent + 2047) / 2048, 1), 592);
+         k_scatter_a_fronts<<<dim3(cnt, gy), 256, 0, s>>>(T, d_fr, st->d_nptr, st->d_nlist, st->d_nrow, nt->d_aval, nt->d_scaling,
                                                 st->d_rlist, st->d_rptr);
          launches += 2;
       }
       if (max_children > 0) {
          {
             ProfScope ps(nt, KC_ZERO);
-            k_zero_contrib<<<dim3(16, cnt), 256, 0, s>>>(T, d_fr);
+            k_zero_contrib<<<dim3(zero_grid_x(maxk), cnt), 256, 0, s>>>(T, d_fr);
             ++launches;
          }
          ProfScope ps(nt, KC_ASSEMBLE);

@@ -449,10 +449,10 @@ static __global__ void k_zero_contrib(DevTree T, const int* __restrict__ fronts)
    const int f = fronts[blockIdx.y];
    if (T.nchild[f] == 0) return;
    const int k = T.m[f] - T.n[f];
-   const size_t tot = (size_t)k * T.ldc[f];
-   double* Cf = T.C + T.coff[f];
-   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
-      Cf[i] = 0.0;
+   const size_t tot2 = ((size_t)k * T.ldc[f]) >> 1;      // ldc is a multiple of 4: whole double2's
+   double2* Cf = reinterpret_cast<double2*>(T.C + T.coff[f]);
+   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot2; i += (size_t)gridDim.x * blockDim.x)
+      Cf[i] = make_double2(0.0, 0.0);
 }
 
 // ---------------------------------------------------------------------------

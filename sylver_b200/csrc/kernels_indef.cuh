@@ -348,18 +348,18 @@ static __global__ void __launch_bounds__(AP_THREADS) k_finish32(DevTree T, TileB
       if (threadIdx.x < wb) perm[threadIdx.x] = operm[lperm[threadIdx.x]];
       double* D = T.D + T.doff[f] + 2 * (size_t)p0;
       if (threadIdx.x < 2 * npass) D[threadIdx.x] = dinv[threadIdx.x];
-      // ---- rows p0..p0+wb of the columns left of the block (both panels) ----
-      for (int c = threadIdx.x; c < 2 * p0; c += AP_THREADS) {
-         double* col = (c < p0 ? Lf + (size_t)c * ldl : Wf + (size_t)(c - p0) * ldl) + p0;
-         double v[IB];
-#pragma unroll
-         for (int i = 0; i < IB; ++i) v[i] = (i < wb) ? col[lperm[i]] : 0.0;
-#pragma unroll
-         for (int i = 0; i < IB; ++i)
-            if (i < wb) col[i] = v[i];
-      }
-      (void)nchunks;
       return;
+   }
+   // ---- rows p0..p0+wb of the columns left of the block (apply_rperm; both panels): the
+   // row chunks share the 2*p0 columns between them ----
+   for (int c = (chunk - 1) * AP_THREADS + threadIdx.x; c < 2 * p0; c += (nchunks - 1) * AP_THREADS) {
+      double* col = (c < p0 ? Lf + (size_t)c * ldl : Wf + (size_t)(c - p0) * ldl) + p0;
+      double v[IB];
+#pragma unroll
+      for (int i = 0; i < IB; ++i) v[i] = (i < wb) ? col[lperm[i]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < IB; ++i)
+         if (i < wb) col[i] = v[i];
    }
    const int r = p0 + wb + (chunk - 1) * AP_THREADS + threadIdx.x;
    if (r >= m) return;
@@ -717,7 +717,7 @@ static __global__ void __launch_bounds__(256) k_init_front(DevTree T, const int*
 }
 
 // A -> front scatter for the fronts of one level (init_a_block, src/kernels/assemble.hxx:162-214).
-// One CTA per front walks its slice of the (src,dest) map.
+// grid (fronts, y): the y CTAs of a front stride its slice of the (src,dest) map.
 static __global__ void __launch_bounds__(256) k_scatter_a_fronts(DevTree T, const int* __restrict__ fronts,
                                                                  const long* __restrict__ nptr,
                                                                  const long* __restrict__ nlist,
@@ -732,7 +732,8 @@ static __global__ void __launch_bounds__(256) k_scatter_a_fronts(DevTree T, cons
    const int ldl = T.ldl[f];
    double* Lf = T.L + T.loff[f];
    const int* rl = rlist + (rptr[f] - 1);
-   for (long e = nptr[f] - 1 + threadIdx.x; e < nptr[f + 1] - 1; e += blockDim.x) {
+   for (long e = nptr[f] - 1 + blockIdx.y * (long)blockDim.x + threadIdx.x; e < nptr[f + 1] - 1;
+        e += (long)gridDim.y * blockDim.x) {
       const long src = nlist[2 * e] - 1;
       const long dest = nlist[2 * e + 1] - 1;
       const int c = (int)(dest / nrow);
