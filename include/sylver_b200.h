@@ -256,6 +256,31 @@ void sylver_b200_set_stream(void *cuda_stream, int enable);
 int sylver_b200_numeric_tree_get_front(void const *tree, int node, int *m, int *n, double *l, double *contrib);
 int sylver_b200_numeric_tree_get_front_indef(void const *tree, int node, int *nelim, double *d, int *perm);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch -------------------------
+ * The reference has no distributed layer (single process, StarPU workers, PCIe staging).
+ * Here every rank runs the same analyse; spldlt_factorize then factorizes the fronts the
+ * deterministic partition (sylver_b200_partition) gives to this rank and moves the
+ * contribution blocks of cross-GPU tree edges with ncclSend/ncclRecv.  spldlt_solve works on a
+ * replicated right-hand side and returns the full solution on every rank.  (Positive
+ * definite factorizations only in this version; posdef=false with world>1 -> flag -98.)
+ *   rank 0:    sylver_b200_comm_unique_id(id)   (128 bytes; broadcast it by any means)
+ *   all ranks: cudaSetDevice(local gpu); sylver_b200_comm_init(rank, world, id)       */
+int sylver_b200_comm_unique_id(void *out128);
+int sylver_b200_comm_init(int rank, int world, void const *id128);
+void sylver_b200_comm_finalize(void);
+int sylver_b200_comm_rank(void);
+int sylver_b200_comm_world(void);
+/* Planning-only communicator (no NCCL object): lets host code inspect what rank `rank` of
+ * `world` would do; numeric calls with it fail. */
+void sylver_b200_comm_set_virtual(int rank, int world);
+/* owner[f] (0-based rank) of every front for `world` GPUs; returns the number of fronts.
+ * Replaces the reference's prune_tree / find_subtree_partition
+ * (src/spldlt_analyse_mod.F90:949-1141,1435-1656): proportional mapping by flops. */
+int sylver_b200_partition(void *akeep, int world, int *owner);
+/* The contribution blocks rank `rank` sends/receives, as quadruples
+ * (level, front, peer, dir: 0 send / 1 recv); returns their number (may exceed cap/4). */
+int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *out);
+
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).
  * a: m x n column-major panel (lda >= m), host memory, overwritten by L;

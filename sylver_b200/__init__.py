@@ -80,6 +80,9 @@ EXPORTS = [
     "sylver_b200_bench_dmma", "sylver_b200_bench_copy", "sylver_b200_akeep_tree",
     "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
     "sylver_b200_numeric_tree_get_front", "sylver_b200_numeric_tree_get_front_indef",
+    "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
+    "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges",
 ]
 
 
@@ -143,6 +146,11 @@ def lib() -> C.CDLL:
     L.sylver_b200_numeric_tree_bytes.restype = C.c_long
     L.sylver_b200_numeric_tree_bytes.argtypes = [vp, lp, lp]
     L.sylver_b200_set_stream.argtypes = [vp, C.c_int]
+    L.sylver_b200_comm_unique_id.argtypes = [vp]
+    L.sylver_b200_comm_init.argtypes = [C.c_int, C.c_int, vp]
+    L.sylver_b200_comm_set_virtual.argtypes = [C.c_int, C.c_int]
+    L.sylver_b200_partition.argtypes = [vp, C.c_int, vp]
+    L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -173,6 +181,41 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)       # raw (device) address
     return a.ctypes.data_as(C.c_void_p)
+
+
+def comm_init_from_torch(dist, device_index: int) -> None:
+    """Create the library's NCCL communicator inside a torch.distributed job (one process
+    per GPU): rank 0 draws the NCCL unique id, torch.distributed broadcasts its 128 bytes."""
+    import torch
+    L = lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        if L.sylver_b200_comm_unique_id(buf) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.to(torch.device("cuda", device_index))
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    idbuf = (C.c_ubyte * 128).from_buffer_copy(raw)
+    if L.sylver_b200_comm_init(rank, world, idbuf) != 0:
+        raise RuntimeError("sylver_b200_comm_init failed")
+
+
+def partition(solver: "Solver", world: int) -> np.ndarray:
+    nn = solver.symbolic()["nnodes"]
+    own = np.zeros(max(nn, 1), dtype=np.int32)
+    lib().sylver_b200_partition(solver.akeep, world, _ptr(own))
+    return own[:nn]
+
+
+def plan_exchanges(solver: "Solver", rank: int, world: int) -> np.ndarray:
+    """(level, front, peer, dir) rows; dir 0 = send, 1 = recv."""
+    cnt = lib().sylver_b200_plan_exchanges(solver.akeep, rank, world, 0, None)
+    out = np.zeros((max(cnt, 1), 4), dtype=np.int32)
+    lib().sylver_b200_plan_exchanges(solver.akeep, rank, world, 4 * cnt, _ptr(out))
+    return out[:cnt]
 
 
 def default_options_c() -> OptionsC:

@@ -12,6 +12,7 @@
 
 #include "../../include/sylver_b200.h"
 #include "analyse.hpp"
+#include "comm.hpp"
 #include "engine.hpp"
 
 using namespace sylver_b200;
@@ -382,6 +383,47 @@ void sylver_b200_set_stream(void* cuda_stream, int enable) { set_user_stream(cud
 int sylver_b200_numeric_tree_get_front(void const* tree, int node, int* m, int* n, double* l, double* contrib) {
    if (!tree) return -1;
    return numeric_tree_get_front(static_cast<const NumericTree*>(tree), node, m, n, l, contrib);
+}
+
+// ------------------------- multi-GPU (one process per GPU) -------------------------
+int sylver_b200_comm_unique_id(void* out128) { return comm_unique_id(out128); }
+int sylver_b200_comm_init(int rank, int world, void const* id128) {
+   if (world < 1 || rank < 0 || rank >= world) return -1;
+   return comm_init(rank, world, id128);
+}
+void sylver_b200_comm_set_virtual(int rank, int world) { comm_set_virtual(rank, world); }
+void sylver_b200_comm_finalize(void) { comm_finalize(); }
+int sylver_b200_comm_rank(void) { return comm().rank; }
+int sylver_b200_comm_world(void) { return comm().world; }
+
+int sylver_b200_partition(void* akeep, int world, int* owner) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   if (!ak || !ak->analysed || !ak->tree) return -1;
+   std::vector<int> own;
+   partition_tree(*ak->tree, world, own);
+   std::copy(own.begin(), own.end(), owner);
+   return (int)own.size();
+}
+
+int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* out) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   if (!ak || !ak->analysed || !ak->tree) return -1;
+   std::vector<int> own;
+   partition_tree(*ak->tree, world, own);
+   std::vector<std::vector<Xfer>> sends, recvs;
+   plan_exchanges(*ak->tree, own, rank, sends, recvs);
+   int cnt = 0;
+   for (int dir = 0; dir < 2; ++dir) {
+      const auto& lists = dir == 0 ? sends : recvs;
+      for (size_t l = 0; l < lists.size(); ++l)
+         for (const Xfer& x : lists[l]) {
+            if (4 * cnt + 3 < cap) {
+               out[4 * cnt] = (int)l; out[4 * cnt + 1] = x.f; out[4 * cnt + 2] = x.peer; out[4 * cnt + 3] = dir;
+            }
+            ++cnt;
+         }
+   }
+   return cnt;
 }
 
 int sylver_b200_numeric_tree_get_front_indef(void const* tree, int node, int* nelim, double* d, int* perm) {

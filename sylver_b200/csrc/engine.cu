@@ -179,26 +179,53 @@ bool numeric_tree_posdef(const NumericTree* nt) { return nt->posdef; }
 void plan_contrib_arena(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
+   const int me = nt->rank;
+   if ((int)nt->owner.size() != N) nt->owner.assign(N, 0);
+   const std::vector<int>& own = nt->owner;
    nt->ldc.resize(N);
    nt->coff.assign(N, 0);
    for (int f = 0; f < N; ++f) nt->ldc[f] = round_up(std::max(st->nrow[f] - st->ncol[f], 1), 4);
    SegAlloc sa;
    for (int l = 0; l < st->nlevels; ++l) {
+      // blocks this rank holds from level l: its own fronts' and remote children of its fronts
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
          const long k = st->nrow[f] - st->ncol[f];
-         if (k > 0) nt->coff[f] = sa.alloc((long)nt->ldc[f] * k);
+         const int p = st->parent[f];
+         const bool held = own[f] == me || (p < N && own[p] == me);
+         if (k > 0 && held) nt->coff[f] = sa.alloc((long)nt->ldc[f] * k);
       }
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
+         if (own[f] != me) continue;
+         // children were consumed by this front's assembly
          for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
             const int c = st->child_list[ci];
             const long k = st->nrow[c] - st->ncol[c];
             if (k > 0) sa.release(nt->coff[c], (long)nt->ldc[c] * k);
          }
+         // a block sent to a remote parent is free once the level's exchange is issued
+         const int p = st->parent[f];
+         const long k = st->nrow[f] - st->ncol[f];
+         if (k > 0 && p < N && own[p] != me) sa.release(nt->coff[f], (long)nt->ldc[f] * k);
       }
    }
    nt->C_doubles = sa.peak + 4;
+}
+
+void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int rank,
+                    std::vector<std::vector<Xfer>>& sends, std::vector<std::vector<Xfer>>& recvs) {
+   const int N = st.nnodes;
+   sends.assign(st.nlevels, {});
+   recvs.assign(st.nlevels, {});
+   for (int l = 0; l < st.nlevels; ++l)
+      for (int i = st.level_ptr[l]; i < st.level_ptr[l + 1]; ++i) {
+         const int f = st.level_nodes[i];
+         const int p = st.parent[f];
+         if (p >= N || st.nrow[f] == st.ncol[f] || owner[f] == owner[p]) continue;
+         if (owner[f] == rank) sends[l].push_back(Xfer{f, owner[p]});
+         else if (owner[p] == rank) recvs[l].push_back(Xfer{f, owner[f]});
+      }
 }
 
 static void build_posdef_plan(NumericTree* nt) {
@@ -207,16 +234,27 @@ static void build_posdef_plan(NumericTree* nt) {
    const int nb = nt->nb;
    nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N);
    nt->loff.resize(N);
+   partition_tree(*st, nt->world, nt->owner);
+   const int me = nt->rank;
    long loff = 0;
    for (int f = 0; f < N; ++f) {
       nt->m[f] = st->nrow[f];
       nt->n[f] = st->ncol[f];
       nt->ldl[f] = round_up(nt->m[f], 4);
       nt->loff[f] = loff;
-      loff += (long)nt->ldl[f] * nt->n[f];
+      if (nt->owner[f] == me) loff += (long)nt->ldl[f] * nt->n[f];
    }
    nt->L_doubles = loff + 4;
    plan_contrib_arena(nt);
+   plan_exchanges(*st, nt->owner, me, nt->sends, nt->recvs);
+   // owned fronts per level (order of st->level_nodes preserved: ncol descending)
+   nt->lvl_ptr.assign(st->nlevels + 1, 0);
+   nt->lvl_nodes.clear();
+   for (int l = 0; l < st->nlevels; ++l) {
+      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i)
+         if (nt->owner[st->level_nodes[i]] == me) nt->lvl_nodes.push_back(st->level_nodes[i]);
+      nt->lvl_ptr[l + 1] = (int)nt->lvl_nodes.size();
+   }
 
    // work lists
    std::vector<int> prefix;
@@ -225,9 +263,9 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->levels.resize(st->nlevels);
    for (int l = 0; l < st->nlevels; ++l) {
       LevelPlan& lp = nt->levels[l];
-      lp.first = st->level_ptr[l];
-      lp.count = st->level_ptr[l + 1] - lp.first;
-      const int* fr = &st->level_nodes[lp.first];
+      lp.first = nt->lvl_ptr[l];
+      lp.count = nt->lvl_ptr[l + 1] - lp.first;
+      const int* fr = nt->lvl_nodes.data() + lp.first;
       lp.max_children = 0;
       int maxn = 0;
       for (int i = 0; i < lp.count; ++i) {
@@ -303,6 +341,7 @@ static void build_posdef_plan(NumericTree* nt) {
    // algorithmic flops per kernel class (lower triangle only, multiply and add counted)
    for (int c = 0; c < KC_COUNT; ++c) nt->prof_flops[c] = 0;
    for (int f = 0; f < N; ++f) {
+      if (nt->owner[f] != me) continue;
       const double m = nt->m[f], n = nt->n[f];
       for (int p0 = 0; p0 < nt->n[f]; p0 += nb) {
          const double pw = std::min(nb, nt->n[f] - p0), p1 = p0 + pw;
@@ -318,6 +357,7 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->W_doubles = wmax;
    nt->d_prefix = dev_upload(prefix);
    nt->d_asm_work = dev_upload(asmw);
+   nt->d_lvl_nodes = dev_upload(nt->lvl_nodes);
 }
 
 void upload_geometry(NumericTree* nt) {
@@ -330,6 +370,27 @@ void upload_geometry(NumericTree* nt) {
    T.loff = nt->d_loff; T.coff = nt->d_coff; T.cmapoff = st->d_cmapoff;
    T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
    T.L = nt->d_L; T.C = nt->d_C;
+}
+
+// Contribution blocks (factorization) or solve work vectors whose parent front lives on another
+// GPU: one NCCL group per level, sends of this rank's fronts and receives for its parents'
+// remote children.  Every rank walks the levels in the same order, so groups pair up.
+// buffer of front f = base + off[f] (+ skip[f] if given), k = m - n doubles per column block.
+static void issue_exchange(NumericTree* nt, int l, double* base, const std::vector<long>& off, const std::vector<int>* skip) {
+   if (nt->world <= 1) return;
+   const auto& sd = nt->sends[l];
+   const auto& rv = nt->recvs[l];
+   if (sd.empty() && rv.empty()) return;
+   SymbolicTree* st = nt->st;
+   auto count = [&](int f) -> size_t {
+      const size_t k = (size_t)(st->nrow[f] - st->ncol[f]);
+      return skip ? k : k * (size_t)nt->ldc[f];
+   };
+   int rc = comm_group_start();
+   for (const Xfer& x : sd) rc |= comm_send(base + off[x.f] + (skip ? (*skip)[x.f] : 0), count(x.f), x.peer, nt->stream);
+   for (const Xfer& x : rv) rc |= comm_recv(base + off[x.f] + (skip ? (*skip)[x.f] : 0), count(x.f), x.peer, nt->stream);
+   rc |= comm_group_end();
+   if (rc) throw CudaFailure{-52};
 }
 
 static void issue_posdef(NumericTree* nt) {
@@ -345,12 +406,17 @@ static void issue_posdef(NumericTree* nt) {
       const int blocks = (int)std::min<long>((st->nent + 255) / 256, 148 * 16);
       ProfScope ps(nt, KC_SCATTER);
       k_scatter_a<<<blocks, 256, 0, s>>>(T, st->nent, st->d_nlist, st->d_anode, st->d_nrow, st->d_ncol,
-                                         nt->d_aval, nt->d_scaling, st->d_rlist, st->d_rptr);
+                                         nt->d_aval, nt->d_scaling, st->d_rlist, st->d_rptr,
+                                         nt->world > 1 ? nt->d_owner : nullptr, nt->rank);
       ++launches;
    }
    for (size_t l = 0; l < nt->levels.size(); ++l) {
       const LevelPlan& lp = nt->levels[l];
-      const int* d_fr = st->d_level_nodes + lp.first;
+      const int* d_fr = nt->d_lvl_nodes + lp.first;
+      if (lp.count == 0) {
+         issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
+         continue;
+      }
       if (lp.max_children > 0) {
          {
             ProfScope ps(nt, KC_ZERO);
@@ -390,7 +456,9 @@ static void issue_posdef(NumericTree* nt) {
          k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0);
          ++launches;
       }
+      issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
    }
+   if (nt->world > 1 && comm_allreduce_max_int(nt->d_fail, 1, s)) throw CudaFailure{-52};
    CU_TRY(cudaGetLastError());
    nt->launches = launches;
 }
@@ -426,10 +494,10 @@ void load_values(NumericTree* nt, const double* aval, const double* scaling) {
 
 static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
    CU_TRY(cudaEventRecord(nt->ev0, nt->stream));
-   if (nt->profile) {
+   if (nt->profile || nt->world > 1) {
       for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
       nt->prof_events.clear();
-      issue_posdef(nt);
+      issue_posdef(nt);      // NCCL exchanges are issued eagerly, level by level
    } else {
       CU_TRY(cudaGraphLaunch(nt->graph, nt->stream));
    }
@@ -469,6 +537,9 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       nt->posdef = posdef;
       nt->opt = *options;
       nt->nb = 128;
+      nt->rank = comm().rank;
+      nt->world = comm().world;
+      if (nt->world > 1 && !posdef) throw CudaFailure{-98};   // multi-GPU APTP: not in this round
       if (g_have_user_stream) {
          nt->stream = g_user_stream;
          nt->own_stream = false;
@@ -493,12 +564,13 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
          return nt;
       }
       build_posdef_plan(nt);
+      if (nt->world > 1) nt->d_owner = dev_upload(nt->owner);
       CU_TRY(cudaMalloc(&nt->d_L, nt->L_doubles * sizeof(double)));
       CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
       CU_TRY(cudaMalloc(&nt->d_W, nt->W_doubles * sizeof(double)));
       upload_geometry(nt);
       // capture the launch sequence once
-      if (!nt->profile) {
+      if (!nt->profile && nt->world == 1) {
          cudaGraph_t g = nullptr;
          CU_TRY(cudaStreamBeginCapture(nt->stream, cudaStreamCaptureModeThreadLocal));
          issue_posdef(nt);
@@ -510,7 +582,8 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       run_posdef(nt, stats);
    } catch (CudaFailure& e) {
       *stats = sylver_inform_c{};
-      stats->flag = (e.code == -98) ? SYLVER_ERROR_UNIMPLEMENTED : SYLVER_ERROR_CUDA_UNKNOWN;
+      stats->flag = (e.code == -98) ? SYLVER_ERROR_UNIMPLEMENTED
+                                    : (e.code == -52 ? SYLVER_ERROR_CUBLAS_UNKNOWN : SYLVER_ERROR_CUDA_UNKNOWN);
       cudaGetLastError();
       if (nt) numeric_tree_destroy(nt);
       return nullptr;
@@ -546,6 +619,7 @@ void numeric_tree_destroy(NumericTree* nt) {
    cudaFree(nt->d_W); cudaFree(nt->d_aval); cudaFree(nt->d_scaling); cudaFree(nt->d_fail);
    cudaFree(nt->d_prefix); cudaFree(nt->d_asm_work); cudaFree(nt->d_xw); cudaFree(nt->d_xwoff);
    cudaFree(nt->d_child_ptr); cudaFree(nt->d_child_list);
+   cudaFree(nt->d_lvl_nodes); cudaFree(nt->d_owner); cudaFree(nt->d_all_nodes); cudaFree(nt->d_xbuf); cudaFree(nt->d_xpack_off);
    if (nt->ev0) cudaEventDestroy(nt->ev0);
    if (nt->ev1) cudaEventDestroy(nt->ev1);
    if (nt->stream && nt->own_stream) cudaStreamDestroy(nt->stream);
@@ -627,8 +701,25 @@ static void ensure_solve_workspace(NumericTree* nt) {
    nt->xwoff[st->nnodes] = off;
    CU_TRY(cudaMalloc(&nt->d_xw, std::max<long>(off, 1) * sizeof(double)));
    nt->d_xwoff = dev_upload(nt->xwoff);
-   nt->d_child_ptr = dev_upload(st->child_ptr);
-   nt->d_child_list = dev_upload(st->child_list);
+   if (!nt->d_child_ptr) nt->d_child_ptr = dev_upload(st->child_ptr);
+   if (!nt->d_child_list) nt->d_child_list = dev_upload(st->child_list);
+   if (nt->world > 1 && !nt->d_all_nodes) {
+      // per-level packing offsets of every front's own variables (solve broadcasts)
+      std::vector<int> off(st->nnodes);
+      size_t cap = 1;
+      for (int l = 0; l < st->nlevels; ++l) {
+         int acc = 0;
+         for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
+            off[i] = acc;
+            acc += st->ncol[st->level_nodes[i]];
+         }
+         cap = std::max(cap, (size_t)acc);
+      }
+      nt->d_all_nodes = dev_upload(st->level_nodes);
+      nt->d_xpack_off = dev_upload(off);
+      nt->xbuf_cap = cap;
+      CU_TRY(cudaMalloc(&nt->d_xbuf, cap * sizeof(double)));
+   }
 }
 
 int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int ldx) {
@@ -666,16 +757,42 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
       const bool do_bwd = (job == 0 || job == 3 || job == 4);
       for (int r = 0; r < nrhs; ++r) {
          a.x = dx + (size_t)r * ldx;
-         if (do_fwd)
+         const bool multi = nt->world > 1;
+         const int* lptr = multi ? nt->lvl_ptr.data() : st->level_ptr.data();
+         const int* d_nodes = multi ? nt->d_lvl_nodes : st->d_level_nodes;
+         if (do_fwd) {
             for (int l = 0; l < st->nlevels; ++l) {
-               const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;
-               k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, st->d_level_nodes + first);
+               const int first = lptr[l], count = lptr[l + 1] - first;
+               if (count > 0) k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
+               // update vectors of fronts whose parent lives on another GPU (rows >= n of xw)
+               if (multi) issue_exchange(nt, l, nt->d_xw, nt->xwoff, &nt->n);
             }
+            if (multi && !do_bwd) {
+               // forward solve only: merge the per-rank pieces into one replicated vector
+               k_zero_unowned<<<st->nnodes, 256, 0, nt->stream>>>(st->nnodes, nt->d_owner, nt->rank, st->d_rlist,
+                                                                   st->d_rptr, st->d_ncol, a.x);
+               if (comm_allreduce_sum(a.x, (size_t)st->n, nt->stream)) throw CudaFailure{-52};
+            }
+         }
          if (do_diag) k_solve_diag<<<(st->nnodes + 7) / 8, 256, 0, nt->stream>>>(a, st->nnodes);
          if (do_bwd)
             for (int l = st->nlevels - 1; l >= 0; --l) {
-               const int first = st->level_ptr[l], count = st->level_ptr[l + 1] - first;
-               k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, st->d_level_nodes + first);
+               const int first = lptr[l], count = lptr[l + 1] - first;
+               if (count > 0) k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
+               if (multi) {
+                  // broadcast the entries solved at this level: pack (zeros for fronts of other
+                  // ranks), all-reduce, unpack into the replicated x
+                  const int af = st->level_ptr[l], ac = st->level_ptr[l + 1] - af;
+                  size_t tot = 0;
+                  for (int i = af; i < af + ac; ++i) tot += st->ncol[st->level_nodes[i]];
+                  k_pack_level<<<ac, 256, 0, nt->stream>>>(nt->d_all_nodes + af, nt->d_xpack_off + af, nt->d_owner,
+                                                           nt->rank, st->d_rlist, st->d_rptr, st->d_ncol, a.x,
+                                                           nt->d_xbuf, 0, nullptr);
+                  if (comm_allreduce_sum(nt->d_xbuf, tot, nt->stream)) throw CudaFailure{-52};
+                  k_pack_level<<<ac, 256, 0, nt->stream>>>(nt->d_all_nodes + af, nt->d_xpack_off + af, nt->d_owner,
+                                                           nt->rank, st->d_rlist, st->d_rptr, st->d_ncol, a.x,
+                                                           nt->d_xbuf, 1, a.x);
+               }
             }
       }
       CU_TRY(cudaGetLastError());

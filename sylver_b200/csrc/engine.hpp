@@ -55,6 +55,17 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
 
 struct NumericTree;
 
+// One contribution block (or solve work vector) crossing GPUs after a level completes.
+struct Xfer {
+   int f;      // front whose generated element travels
+   int peer;   // the other rank
+};
+// Deterministic mapping of fronts to ranks and the resulting per-level exchange lists
+// (host only; identical on every rank).
+void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner);
+void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int rank,
+                    std::vector<std::vector<Xfer>>& sends, std::vector<std::vector<Xfer>>& recvs);
+
 NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* aval, const double* scaling,
                                  const sylver_options_c* options, sylver_inform_c* stats);
 // Re-run the factorization with new values on an existing tree (same plan).

@@ -9,6 +9,7 @@
 #include <map>
 #include <vector>
 
+#include "comm.hpp"
 #include "engine.hpp"
 #include "kernels.cuh"
 
@@ -120,6 +121,7 @@ enum KClass { KC_SCATTER = 0, KC_ZERO, KC_ASSEMBLE, KC_POTRF, KC_TRSM, KC_UPDATE
 
 
 struct NumericTree {
+   using Xfer = ::sylver_b200::Xfer;
    SymbolicTree* st = nullptr;
    bool posdef = true;
    sylver_options_c opt{};
@@ -156,6 +158,16 @@ struct NumericTree {
    long* d_xwoff = nullptr;
    std::vector<long> xwoff;
    int* d_child_ptr = nullptr; int* d_child_list = nullptr;
+   // ---- multi-GPU (one process per GPU): fronts owned by this rank, exchanges per level ----
+   int rank = 0, world = 1;
+   std::vector<int> owner;               // rank owning each front (partition_tree)
+   std::vector<int> lvl_ptr, lvl_nodes;  // owned fronts grouped by level (ncol descending)
+   int* d_lvl_nodes = nullptr;
+   std::vector<std::vector<Xfer>> sends, recvs;   // per level: contribution blocks crossing GPUs
+   int* d_owner = nullptr;
+   int* d_all_nodes = nullptr;           // st->level_nodes (all fronts), for the solve broadcasts
+   int* d_xpack_off = nullptr;
+   double* d_xbuf = nullptr; size_t xbuf_cap = 0;
    // ---- indefinite (APTP) path: dynamic geometry, see engine_indef.cu ----
    struct Chunk { double* ptr; size_t cap, used; };
    std::vector<Chunk> chunks;            // factor arena: L panel + D^-1 + perm per front, bump allocated
@@ -194,6 +206,9 @@ struct ProfScope {
 };
 }  // namespace
 
+
+// partition.cpp
+void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner);
 
 // engine_indef.cu
 void run_indef(NumericTree* nt, sylver_inform_c* stats);

@@ -425,9 +425,10 @@ static __global__ void k_scatter_a(DevTree T, long nent, const long* __restrict_
                             const int* __restrict__ anode, const int* __restrict__ nrow0,
                             const int* __restrict__ ncol0, const double* __restrict__ aval,
                             const double* __restrict__ scaling, const int* __restrict__ rlist,
-                            const long* __restrict__ rptr) {
+                            const long* __restrict__ rptr, const int* __restrict__ owner, int me) {
    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
       const int f = anode[e];
+      if (owner && owner[f] != me) continue;      // multi-GPU: only the fronts this rank factorizes
       const long src = nlist[2 * e] - 1;
       const long dest = nlist[2 * e + 1] - 1;
       const int nrow = nrow0[f];

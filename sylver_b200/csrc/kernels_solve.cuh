@@ -130,6 +130,35 @@ static __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_bwd(SolveArgs a,
    for (int i = tid; i < ne; i += SOLVE_THREADS) a.x[var_index(a, f, i, rl)] = xw[i];
 }
 
+// ---- multi-GPU solve (positive definite): x is replicated; the variables a front eliminates
+// are the contiguous range x[v0, v0 + ncol), v0 = rlist[rptr[f]-1] - 1 ----
+// pack: buf[off[i] + j] = (front owned by `me`) ? x[v0 + j] : 0, one CTA per front of the level;
+// after an all-reduce(sum) of buf every rank unpacks the freshly solved entries.
+static __global__ void __launch_bounds__(256) k_pack_level(const int* __restrict__ fronts, const int* __restrict__ off,
+                                                           const int* __restrict__ owner, int me,
+                                                           const int* __restrict__ rlist, const long* __restrict__ rptr,
+                                                           const int* __restrict__ ncol, const double* __restrict__ x,
+                                                           double* __restrict__ buf, int unpack, double* __restrict__ xout) {
+   const int f = fronts[blockIdx.x];
+   const int v0 = rlist[rptr[f] - 1] - 1;
+   const int nc = ncol[f];
+   double* b = buf + off[blockIdx.x];
+   if (unpack) {
+      for (int j = threadIdx.x; j < nc; j += blockDim.x) xout[v0 + j] = b[j];
+   } else {
+      const bool mine = owner[f] == me;
+      for (int j = threadIdx.x; j < nc; j += blockDim.x) b[j] = mine ? x[v0 + j] : 0.0;
+   }
+}
+static __global__ void __launch_bounds__(256) k_zero_unowned(int nfronts, const int* __restrict__ owner, int me,
+                                                             const int* __restrict__ rlist, const long* __restrict__ rptr,
+                                                             const int* __restrict__ ncol, double* __restrict__ x) {
+   const int f = blockIdx.x;
+   if (f >= nfronts || owner[f] == me) return;
+   const int v0 = rlist[rptr[f] - 1] - 1;
+   for (int j = threadIdx.x; j < ncol[f]; j += blockDim.x) x[v0 + j] = 0.0;
+}
+
 // D^-1 application of every front (indefinite only; ldlt_app_solve_diag,
 // spral/src/ssids/cpu/kernels/ldlt_app.cxx:2556-2578).  One warp per front.
 static __global__ void __launch_bounds__(256) k_solve_diag(SolveArgs a, int nfronts) {

@@ -1,0 +1,143 @@
+// Mapping of the assembly tree onto the GPUs of one box (host code, deterministic: every
+// rank computes the same map from the same symbolic tree, nothing is communicated).
+//
+// The reference balances pruned subtrees over its workers by flops with a greedy
+// "heaviest first onto the least loaded" rule (prune_tree,
+// src/spldlt_analyse_mod.F90:1435-1656, weights compute_flops :1744-1764) and keeps the top
+// of the tree on the CPU.  Here the whole tree lives on GPUs: a proportional
+// (subtree-to-subcube) mapping hands each child subtree a share of its parent's rank group
+// in proportion to its flops; subtrees that are too light to deserve a rank of their own are
+// packed whole onto the least loaded rank of the group (the reference's greedy rule); the
+// fronts above the cut are owned by the least loaded rank of their group.  NVSwitch gives
+// uniform bandwidth between any two GPUs, so the mapping optimises load only.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace sylver_b200 {
+
+namespace {
+struct Mapper {
+   const SymbolicTree& st;
+   std::vector<double> wsub;      // flops of the subtree rooted at each front
+   std::vector<double> wown;      // flops of the front itself
+   std::vector<double> load;      // per rank
+   std::vector<int>& owner;
+   std::vector<std::pair<int, std::pair<int, int>>> top;   // (front, rank group) above the cut, top-down
+
+   void assign_subtree(int f, int r) {
+      // iterative DFS: the whole subtree goes to rank r
+      std::vector<int> stack{f};
+      while (!stack.empty()) {
+         const int g = stack.back();
+         stack.pop_back();
+         owner[g] = r;
+         for (int ci = st.child_ptr[g]; ci < st.child_ptr[g + 1]; ++ci) stack.push_back(st.child_list[ci]);
+      }
+      load[r] += wsub[f];
+   }
+
+   int least_loaded(int r0, int r1) const {
+      int best = r0;
+      for (int r = r0 + 1; r < r1; ++r)
+         if (load[r] < load[best]) best = r;
+      return best;
+   }
+
+   // distribute the children of `f` (or the roots when f == nnodes) over ranks [r0, r1)
+   void map_children(int f, int r0, int r1) {
+      struct Item { int f, r0, r1; };
+      std::vector<Item> work{{f, r0, r1}};
+      while (!work.empty()) {
+         const Item it = work.back();
+         work.pop_back();
+         const int nr = it.r1 - it.r0;
+         std::vector<int> ch(st.child_list.begin() + st.child_ptr[it.f], st.child_list.begin() + st.child_ptr[it.f + 1]);
+         if (ch.empty()) continue;
+         std::stable_sort(ch.begin(), ch.end(), [&](int a, int b) { return wsub[a] > wsub[b]; });
+         double tot = 0;
+         for (int c : ch) tot += wsub[c];
+         if (nr == 1 || tot <= 0) {
+            for (int c : ch) assign_subtree(c, it.r0);
+            continue;
+         }
+         // children heavy enough for ranks of their own ("big"), at most nr of them
+         std::vector<int> big;
+         for (int c : ch)
+            if ((int)big.size() < nr && wsub[c] * nr >= 0.75 * tot) big.push_back(c);
+         if (big.empty()) {
+            for (int c : ch) assign_subtree(c, least_loaded(it.r0, it.r1));
+            continue;
+         }
+         // ranks per big child: largest remainder on shares proportional to flops, >= 1 each
+         double btot = 0;
+         for (int c : big) btot += wsub[c];
+         std::vector<int> share(big.size());
+         std::vector<std::pair<double, int>> rem;
+         int used = 0;
+         for (size_t i = 0; i < big.size(); ++i) {
+            const double s = nr * wsub[big[i]] / btot;
+            share[i] = std::max(1, (int)std::floor(s));
+            used += share[i];
+            rem.emplace_back(s - std::floor(s), (int)i);
+         }
+         std::stable_sort(rem.begin(), rem.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+            return a.first > b.first;
+         });
+         for (size_t i = 0; used < nr; ++i, ++used) share[rem[i % rem.size()].second]++;
+         for (size_t i = big.size(); used > nr && i-- > 0;)
+            while (share[i] > 1 && used > nr) { --share[i]; --used; }
+         int r = it.r0;
+         for (size_t i = 0; i < big.size(); ++i) {
+            const int c = big[i];
+            if (share[i] == 1) {
+               assign_subtree(c, r);
+            } else {
+               top.push_back({c, {r, r + share[i]}});
+               work.push_back({c, r, r + share[i]});
+            }
+            r += share[i];
+         }
+         // the light children are packed afterwards (loads of the big ones are only known
+         // once their recursion bottomed out; pack onto currently least loaded rank)
+         for (int c : ch)
+            if (std::find(big.begin(), big.end(), c) == big.end()) assign_subtree(c, least_loaded(it.r0, it.r1));
+      }
+   }
+};
+}  // namespace
+
+// owner[f] in [0, world) for every front.  world == 1 maps everything to rank 0.
+void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner) {
+   const int N = st.nnodes;
+   owner.assign(N, 0);
+   if (world <= 1 || N == 0) return;
+   std::vector<double> wown(N), wsub(N);
+   for (int f = 0; f < N; ++f) {
+      const double mm = st.nrow[f] - st.ncol[f], n = st.ncol[f];
+      // sum_{j=1..n} (mm + j)^2
+      wown[f] = n * mm * mm + mm * n * (n + 1) + n * (n + 1) * (2 * n + 1) / 6.0;
+      wsub[f] = wown[f];
+   }
+   for (int f = 0; f < N; ++f) {      // children precede parents
+      const int p = st.parent[f];
+      if (p < N) wsub[p] += wsub[f];
+   }
+   std::vector<int> own(N, -1);
+   Mapper mp{st, wsub, wown, std::vector<double>(world, 0.0), own, {}};
+   mp.map_children(N, 0, world);       // children of the virtual root
+   // fronts above the cut: bottom-up (reverse of discovery is not level order; sort by index,
+   // children have smaller indices), least loaded rank of the group
+   std::sort(mp.top.begin(), mp.top.end());
+   for (auto& t : mp.top) {
+      const int r = mp.least_loaded(t.second.first, t.second.second);
+      own[t.first] = r;
+      mp.load[r] += wown[t.first];
+   }
+   for (int f = 0; f < N; ++f) owner[f] = own[f] < 0 ? 0 : own[f];
+}
+
+}  // namespace sylver_b200
