@@ -322,6 +322,31 @@ static void build_posdef_plan(NumericTree* nt) {
          }
          prefix.push_back(acc);
          ls.upd_tiles = acc;
+         // look-ahead split of the same tiles: first tile column (TR tiles) / the rest
+         ls.updn_prefix = prefix.size();
+         acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int base = p0 + std::min(nb, nt->n[f] - p0);
+            prefix.push_back(acc);
+            if (nt->n[f] > base) acc += (nt->m[f] - base + GT_BM - 1) / GT_BM;
+         }
+         prefix.push_back(acc);
+         ls.updn_tiles = acc;
+         ls.updr_prefix = prefix.size();
+         acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int base = p0 + std::min(nb, nt->n[f] - p0);
+            prefix.push_back(acc);
+            if (nt->n[f] > base) {
+               const int TR = (nt->m[f] - base + GT_BM - 1) / GT_BM;
+               const int TC = (nt->n[f] - base + GT_BN - 1) / GT_BN;
+               for (int tj = 1; tj < TC; ++tj) acc += TR - tj;
+            }
+         }
+         prefix.push_back(acc);
+         ls.updr_tiles = acc;
       }
       // contribution tiles
       lp.contrib_prefix = prefix.size();
@@ -430,24 +455,62 @@ static void issue_posdef(NumericTree* nt) {
             ++launches;
          }
       }
-      for (size_t si = 0; si < lp.steps.size(); ++si) {
+      auto potrf = [&](size_t si, cudaStream_t q) {
          const LevelStep& ls = lp.steps[si];
-         {
-            ProfScope ps(nt, KC_POTRF);
-            k_potrf_inv<<<ls.cnt, PF_THREADS, PF_SMEM_BYTES, s>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
-         }
+         ProfScope ps(nt, KC_POTRF, q);
+         if (ls.wld <= 32)
+            k_potrf_inv<32><<<ls.cnt, 128, PotrfCfg<32>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         else if (ls.wld <= 64)
+            k_potrf_inv<64><<<ls.cnt, 256, PotrfCfg<64>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         else
+            k_potrf_inv<128><<<ls.cnt, 512, PotrfCfg<128>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
          ++launches;
-         if (ls.trsm_tiles > 0) {
-            TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
-            ProfScope ps(nt, KC_TRSM);
-            k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld);
-            ++launches;
+      };
+      auto trsm = [&](size_t si, cudaStream_t q) {
+         const LevelStep& ls = lp.steps[si];
+         if (ls.trsm_tiles == 0) return;
+         TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
+         ProfScope ps(nt, KC_TRSM, q);
+         k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld);
+         ++launches;
+      };
+      auto update = [&](size_t si, int sub, cudaStream_t q) {
+         const LevelStep& ls = lp.steps[si];
+         const int tiles = sub == 0 ? ls.upd_tiles : (sub == 1 ? ls.updn_tiles : ls.updr_tiles);
+         if (tiles == 0) return;
+         const size_t off = sub == 0 ? ls.upd_prefix : (sub == 1 ? ls.updn_prefix : ls.updr_prefix);
+         TileBatch b{d_fr, nt->d_prefix + off, ls.cnt};
+         ProfScope ps(nt, KC_UPDATE, q);
+         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, (int)si, nb, nullptr, sub);
+         ++launches;
+      };
+      // Look-ahead (few, large fronts): as soon as the next block column has received its
+      // update, its diagonal-block factorization and panel solve run on a second stream beside
+      // the rest of the trailing update, taking the latency-bound potrf off the critical path.
+      const bool lookahead = nt->stream2 && lp.steps.size() >= 2 && lp.count <= 16;
+      if (!lookahead) {
+         for (size_t si = 0; si < lp.steps.size(); ++si) {
+            potrf(si, s);
+            trsm(si, s);
+            update(si, 0, s);
          }
-         if (ls.upd_tiles > 0) {
-            TileBatch b{d_fr, nt->d_prefix + ls.upd_prefix, ls.cnt};
-            ProfScope ps(nt, KC_UPDATE);
-            k_gemm_batched<<<ls.upd_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, (int)si, nb, nullptr, 0);
-            ++launches;
+      } else {
+         cudaStream_t s2 = nt->stream2;
+         potrf(0, s);
+         trsm(0, s);
+         for (size_t si = 0; si < lp.steps.size(); ++si) {
+            if (si + 1 < lp.steps.size()) {
+               update(si, 1, s);
+               CU_TRY(cudaEventRecord(nt->ev_next, s));
+               CU_TRY(cudaStreamWaitEvent(s2, nt->ev_next, 0));
+               potrf(si + 1, s2);
+               trsm(si + 1, s2);
+               CU_TRY(cudaEventRecord(nt->ev_panel, s2));
+               update(si, 2, s);
+               CU_TRY(cudaStreamWaitEvent(s, nt->ev_panel, 0));
+            } else {
+               update(si, 0, s);
+            }
          }
       }
       if (lp.contrib_tiles > 0) {
@@ -467,7 +530,9 @@ static void set_kernel_attributes() {
    static bool done = false;
    if (done) return;
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
-   CU_TRY(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_potrf_inv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<128>::SMEM));
+   CU_TRY(cudaFuncSetAttribute(k_potrf_inv<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<64>::SMEM));
+   CU_TRY(cudaFuncSetAttribute(k_potrf_inv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<32>::SMEM));
    done = true;
 }
 
@@ -552,6 +617,14 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       }
       CU_TRY(cudaEventCreate(&nt->ev0));
       CU_TRY(cudaEventCreate(&nt->ev1));
+      {
+         const char* la = getenv("SYLVER_B200_LOOKAHEAD");
+         if (!(la && la[0] == '0')) {
+            CU_TRY(cudaStreamCreateWithFlags(&nt->stream2, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&nt->ev_next, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&nt->ev_panel, cudaEventDisableTiming));
+         }
+      }
       CU_TRY(cudaMalloc(&nt->d_fail, 4 * sizeof(int)));
       // values: the map references entries 1..max(src)
       nt->aval_count = (size_t)st->nval;
@@ -623,6 +696,9 @@ void numeric_tree_destroy(NumericTree* nt) {
    if (nt->ev0) cudaEventDestroy(nt->ev0);
    if (nt->ev1) cudaEventDestroy(nt->ev1);
    if (nt->stream && nt->own_stream) cudaStreamDestroy(nt->stream);
+   if (nt->stream2) cudaStreamDestroy(nt->stream2);
+   if (nt->ev_next) cudaEventDestroy(nt->ev_next);
+   if (nt->ev_panel) cudaEventDestroy(nt->ev_panel);
    for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
    delete nt;
 }

@@ -106,6 +106,8 @@ struct LevelStep {
    int wld;             // stride of the inverse slots for this step
    int trsm_tiles, upd_tiles;
    size_t trsm_prefix, upd_prefix;   // offsets into d_prefix
+   int updn_tiles = 0, updr_tiles = 0;      // look-ahead split: first tile column / the rest
+   size_t updn_prefix = 0, updr_prefix = 0;
 };
 struct LevelPlan {
    int first, count;               // range in level_nodes
@@ -143,6 +145,8 @@ struct NumericTree {
    DevTree T{};
    cudaStream_t stream = nullptr;
    bool own_stream = true;
+   cudaStream_t stream2 = nullptr;       // look-ahead: next panel's potrf + solve run beside the update
+   cudaEvent_t ev_next = nullptr, ev_panel = nullptr;
    cudaGraphExec_t graph = nullptr;
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
    bool profile = false;
@@ -193,14 +197,15 @@ struct NumericTree {
 namespace {
 struct ProfScope {
    NumericTree* nt; int cls; cudaEvent_t a = nullptr, b = nullptr;
-   ProfScope(NumericTree* nt_, int cls_) : nt(nt_), cls(cls_) {
+   cudaStream_t st;
+   ProfScope(NumericTree* nt_, int cls_, cudaStream_t s_ = nullptr) : nt(nt_), cls(cls_), st(s_ ? s_ : nt_->stream) {
       if (!nt->profile) return;
       cudaEventCreate(&a); cudaEventCreate(&b);
-      cudaEventRecord(a, nt->stream);
+      cudaEventRecord(a, st);
    }
    ~ProfScope() {
       if (!nt->profile) return;
-      cudaEventRecord(b, nt->stream);
+      cudaEventRecord(b, st);
       nt->prof_events.push_back({cls, {a, b}});
    }
 };

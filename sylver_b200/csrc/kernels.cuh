@@ -274,7 +274,9 @@ __device__ __forceinline__ int find_front(const TileBatch& b, int item) {
 // mode 1: contribution block:  C[r-n][c-n] = beta*C - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
 // mode 2: panel solve with the inverted diagonal block W (pw x pw, ld wld):
 //         L[r][p0+c] = sum_k L[r][p0+k] W[c][k],  r in [p0+pw, m)
-// nb is the block-column width; `step` the block column index.
+// nb is the block-column width; `step` the block column index.  For mode 0, `wld` selects a
+// subset of the trailing tiles (look-ahead scheduling): 0 all, 1 only the first tile column
+// (the next block column), 2 everything but the first tile column.
 static __global__ void __launch_bounds__(GT_THREADS, 1)
 k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld) {
    extern __shared__ __align__(128) double smem[];
@@ -348,6 +350,7 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       const int cend = (mode == 0) ? n : m;
       const int TR = (m - base + GT_BM - 1) / GT_BM;
       const int TC = (cend - base + GT_BN - 1) / GT_BN;
+      if (mode == 0 && wld == 2) local += TR;       // skip the first tile column
       int tj = 0;
       while (tj < TC && local >= TR - tj) { local -= TR - tj; ++tj; }
       const int ti = tj + local;
@@ -489,73 +492,86 @@ static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* 
 }
 
 // ---------------------------------------------------------------------------
-// Cholesky of one diagonal block (pw <= 128) per CTA, plus its explicit
-// inverse W = L_jj^{-1} (lower, ld 128) used by the DMMA panel solve.
-// Replaces factorize_diag_block (reference src/kernels/factor.hxx:34-88; LAPACK
-// dpotrf there).  A non-positive pivot records (front, column) in `fail`.
+// Cholesky of one diagonal block (pw <= PW) per CTA, plus its explicit inverse
+// W = L_jj^{-1} (lower) used by the DMMA panel solve.  Replaces factorize_diag_block
+// (reference src/kernels/factor.hxx:34-88; LAPACK dpotrf there).  A non-positive pivot
+// records (front, column) in `fail`.
+//
+// Three template sizes (32/64/128) so that the thousands of small fronts of the lower tree
+// levels do not pay for a 200 KB shared-memory footprint (several CTAs per SM there).
 // ---------------------------------------------------------------------------
-constexpr int PF_LD = 129;
-constexpr int PF_THREADS = 512;
-constexpr int PF_VPACK = 128 * 129 / 2;   // packed lower triangle of the inverse
-constexpr size_t PF_SMEM_BYTES = ((size_t)128 * PF_LD + PF_VPACK + 128) * sizeof(double);
+constexpr int PF_THREADS = 512;      // PW = 128 variant (threads = 4 * PW)
+template <int PW>
+struct PotrfCfg {
+   static constexpr int LD = PW + 1;
+   static constexpr int NT = 4 * PW;
+   static constexpr int VPACK = PW * (PW + 1) / 2;
+   static constexpr size_t SMEM = ((size_t)PW * LD + VPACK + PW) * sizeof(double);
+};
+constexpr size_t PF_SMEM_BYTES = PotrfCfg<128>::SMEM;
 // packed column-major lower triangle: element (i,j), i >= j
-__device__ __forceinline__ int vpk(int i, int j) { return j * 128 - (j * (j - 1)) / 2 + (i - j); }
+template <int PW>
+__device__ __forceinline__ int vpk(int i, int j) { return j * PW - (j * (j - 1)) / 2 + (i - j); }
 
-static __global__ void __launch_bounds__(PF_THREADS, 1)
+template <int PW>
+static __global__ void __launch_bounds__(4 * PW, 1)
 k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double* __restrict__ W, int wld,
             int* fail) {
+   using Cfg = PotrfCfg<PW>;
+   constexpr int LD = Cfg::LD, NT = Cfg::NT, NW = NT / 32;
    extern __shared__ __align__(16) double sm[];
-   double* S = sm;                    // S[r + c*PF_LD]
-   double* V = sm + 128 * PF_LD;      // inverse, packed lower triangle
-   double* rd = V + PF_VPACK;         // reciprocal diagonal
+   double* S = sm;                    // S[r + c*LD]
+   double* V = sm + PW * LD;          // inverse, packed lower triangle
+   double* rd = V + Cfg::VPACK;       // reciprocal diagonal
    const int f = fronts[blockIdx.x];
    const int n = T.n[f], ldl = T.ldl[f];
    const int p0 = step * nb;
    const int pw = min(nb, n - p0);
    double* A = T.L + T.loff[f] + (size_t)p0 * ldl + p0;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   constexpr int NW = PF_THREADS / 32;
    for (int c = warp; c < pw; c += NW)
-      for (int r = lane; r < pw; r += 32) S[r + c * PF_LD] = (r >= c) ? A[(size_t)c * ldl + r] : 0.0;
+      for (int r = lane; r < pw; r += 32) S[r + c * LD] = (r >= c) ? A[(size_t)c * ldl + r] : 0.0;
    __syncthreads();
    // right-looking Cholesky, 2 barriers per column; warp w updates columns k+1+w, k+1+w+NW, ...
+   // (a blocked variant with a register-resident 32x32 warp factorization was measured 1.5x
+   // SLOWER: the single-warp sections are latency bound at ~12 cycles per instruction)
    for (int k = 0; k < pw; ++k) {
-      const double akk = S[k + k * PF_LD];
+      const double akk = S[k + k * LD];
       const bool ok = akk > 0.0;
       if (!ok && tid == 0) {
          atomicExch(&fail[0], 1);
          atomicMin(&fail[1], f);
       }
-      const double d = ok ? sqrt(akk) : 1.0;
-      const double rinv = 1.0 / d;
+      const double rinv = ok ? rsqrt(akk) : 1.0;
+      const double d = ok ? akk * rinv : 1.0;
       __syncthreads();
-      for (int r = k + tid; r < pw; r += PF_THREADS) S[r + k * PF_LD] = (r == k) ? d : S[r + k * PF_LD] * rinv;
+      for (int r = k + tid; r < pw; r += NT) S[r + k * LD] = (r == k) ? d : S[r + k * LD] * rinv;
       __syncthreads();
       for (int c = k + 1 + warp; c < pw; c += NW) {
-         const double lck = S[c + k * PF_LD];
-         for (int r = c + lane; r < pw; r += 32) S[r + c * PF_LD] -= S[r + k * PF_LD] * lck;
+         const double lck = S[c + k * LD];
+         for (int r = c + lane; r < pw; r += 32) S[r + c * LD] -= S[r + k * LD] * lck;
       }
    }
    __syncthreads();
    for (int c = warp; c < pw; c += NW)
-      for (int r = c + lane; r < pw; r += 32) A[(size_t)c * ldl + r] = S[r + c * PF_LD];
-   for (int i = tid; i < pw; i += PF_THREADS) rd[i] = 1.0 / S[i + i * PF_LD];
+      for (int r = c + lane; r < pw; r += 32) A[(size_t)c * ldl + r] = S[r + c * LD];
+   for (int i = tid; i < pw; i += NT) rd[i] = 1.0 / S[i + i * LD];
    __syncthreads();
    // Inverse by forward substitution: 4 lanes cooperate on one column j of V (L v = e_j),
    // splitting each dot product; no block barrier is needed inside a column.
    {
       const int q = tid & 3;
-      for (int j = tid >> 2; j < 128; j += PF_THREADS / 4) {
+      for (int j = tid >> 2; j < PW; j += NT / 4) {
          if (j >= pw) continue;     // whole quad skips together (same j)
-         if (q == 0) V[vpk(j, j)] = rd[j];
+         if (q == 0) V[vpk<PW>(j, j)] = rd[j];
          __syncwarp(0xFu << (lane & ~3));
          for (int i = j + 1; i < pw; ++i) {
             double s = 0.0;
-            const double* vj = V + vpk(j, j) - j;      // vj[kk] = V(kk, j)
-            for (int kk = j + q; kk < i; kk += 4) s += S[i + kk * PF_LD] * vj[kk];
+            const double* vj = V + vpk<PW>(j, j) - j;      // vj[kk] = V(kk, j)
+            for (int kk = j + q; kk < i; kk += 4) s += S[i + kk * LD] * vj[kk];
             s += __shfl_xor_sync(0xFu << (lane & ~3), s, 1);
             s += __shfl_xor_sync(0xFu << (lane & ~3), s, 2);
-            if (q == 0) V[vpk(i, j)] = -s * rd[i];
+            if (q == 0) V[vpk<PW>(i, j)] = -s * rd[i];
             __syncwarp(0xFu << (lane & ~3));
          }
       }
@@ -563,7 +579,8 @@ k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double*
    __syncthreads();
    double* Wf = W + (size_t)blockIdx.x * wld * wld;
    for (int c = warp; c < wld; c += NW)
-      for (int r = lane; r < wld; r += 32) Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[vpk(r, c)] : 0.0;
+      for (int r = lane; r < wld; r += 32)
+         Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[vpk<PW>(r, c)] : 0.0;
 }
 
 }  // namespace sylver_b200
