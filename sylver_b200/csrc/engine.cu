@@ -442,19 +442,15 @@ static void issue_posdef(NumericTree* nt) {
          issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
          continue;
       }
-      if (lp.max_children > 0) {
-         {
-            ProfScope ps(nt, KC_ZERO);
-            k_zero_contrib<<<dim3(zero_grid_x(lp.max_contrib), lp.count), 256, 0, s>>>(T, d_fr);
-         }
-         ++launches;
+      auto assemble = [&](int part) {
          for (auto& w : lp.asm_work) {
             if (w.second == 0) continue;
             ProfScope ps(nt, KC_ASSEMBLE);
-            k_assemble<<<w.second, 256, 0, s>>>(T, nt->d_asm_work + w.first);
+            k_assemble<<<w.second, 256, 0, s>>>(T, nt->d_asm_work + w.first, part);
             ++launches;
          }
-      }
+      };
+      assemble(0);      // children -> fully-summed columns
       auto potrf = [&](size_t si, cudaStream_t q) {
          const LevelStep& ls = lp.steps[si];
          ProfScope ps(nt, KC_POTRF, q);
@@ -519,6 +515,7 @@ static void issue_posdef(NumericTree* nt) {
          k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0);
          ++launches;
       }
+      assemble(1);      // children -> contribution block (after this front's own Schur complement)
       issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
    }
    if (nt->world > 1 && comm_allreduce_max_int(nt->d_fail, 1, s)) throw CudaFailure{-52};

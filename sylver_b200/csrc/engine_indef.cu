@@ -291,22 +291,18 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                                                 st->d_rlist, st->d_rptr);
          launches += 2;
       }
-      if (max_children > 0) {
-         {
-            ProfScope ps(nt, KC_ZERO);
-            k_zero_contrib<<<dim3(zero_grid_x(maxk), cnt), 256, 0, s>>>(T, d_fr);
-            ++launches;
-         }
+      auto assemble = [&](int part) {
          ProfScope ps(nt, KC_ASSEMBLE);
          for (auto& w : asm_ranges) {
             if (w.second == 0) continue;
-            k_assemble_indef<<<w.second, 256, 0, s>>>(T, d_asm + w.first);
+            k_assemble_indef<<<w.second, 256, 0, s>>>(T, d_asm + w.first, part);
             ++launches;
          }
-         if (!delay_work.empty()) {
-            k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
-            ++launches;
-         }
+      };
+      assemble(0);
+      if (!delay_work.empty()) {
+         k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
+         ++launches;
       }
       // ---- APTP block columns ----
       const int nsteps = (maxn + IB - 1) / IB;
@@ -342,6 +338,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0);
          ++launches;
       }
+      assemble(1);
       k_front_stats<<<(cnt + 127) / 128, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out);
       k_copy_nelim<<<(cnt + 255) / 256, 256, 0, s>>>(d_fr, nt->d_lvl_out, cnt, nt->d_nelim);
       launches += 2;

@@ -328,9 +328,8 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       } else {
          const int ldc = T.ldc[f];
          dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
-         op = (T.nchild[f] > 0) ? 0 : 1;
-         if (op == 0 && t.K == 0) return;
-         t.prefetch = (op == 0);
+         op = 1;      // children are extend-added afterwards (k_assemble_indef part 1)
+         t.prefetch = false;
       }
    } else if (mode == 2) {
       // tile origin rounded down to an even row so the TMA source stays 16 B aligned
@@ -369,8 +368,8 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       } else {
          const int ldc = T.ldc[f];
          dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
-         op = (T.nchild[f] > 0) ? 0 : 1;     // children were extend-added before the factorization
-         t.prefetch = (op == 0);
+         op = 1;      // children are extend-added afterwards (k_assemble part 1)
+         t.prefetch = false;
       }
    }
    t.dst = dbase + (size_t)j0 * ldd + i0;
@@ -448,17 +447,6 @@ static __global__ void k_scatter_a(DevTree T, long nent, const long* __restrict_
    }
 }
 
-// Zero the contribution blocks of fronts that will receive children.
-static __global__ void k_zero_contrib(DevTree T, const int* __restrict__ fronts) {
-   const int f = fronts[blockIdx.y];
-   if (T.nchild[f] == 0) return;
-   const int k = T.m[f] - T.n[f];
-   const size_t tot2 = ((size_t)k * T.ldc[f]) >> 1;      // ldc is a multiple of 4: whole double2's
-   double2* Cf = reinterpret_cast<double2*>(T.C + T.coff[f]);
-   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot2; i += (size_t)gridDim.x * blockDim.x)
-      Cf[i] = make_double2(0.0, 0.0);
-}
-
 // ---------------------------------------------------------------------------
 // Extend-add of one child's contribution block into its parent front.
 // Replaces assemble_block / assemble_contrib_block (reference
@@ -470,24 +458,40 @@ static __global__ void k_zero_contrib(DevTree T, const int* __restrict__ fronts)
 // work item = (child, first column of a 32-column chunk); warp w takes columns
 // w, w+8, ...; lanes stride over rows (coalesced reads of the child block).
 // ---------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* __restrict__ work) {
+// part 0: columns that land in the parent's fully-summed (L) panel -- before the parent is
+//         factorized;  part 1: columns that land in the parent's contribution block -- after
+//         the parent's own Schur complement has been written there (the reference's order:
+//         assemble_contrib follows factor_front, src/NumericTreePosdef.hxx:276-321), so the
+//         contribution block needs no zero fill and the DMMA epilogue never reads it.
+static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* __restrict__ work, int part) {
    const int2 w = work[blockIdx.x];
    const int c = w.x;
    const int p = T.parent[c];
    const int k = T.m[c] - T.n[c];
    const int* cm = T.cmap + T.cmapoff[c];
+   const int pn = T.n[p];
+   const int jend = min(k, w.y + 32);
+   // cm is increasing: the chunk is skipped as a whole when it lies in the other part
+   if (part == 0 ? (cm[w.y] >= pn) : (cm[jend - 1] < pn)) return;
    const double* src = T.C + T.coff[c];
    const int ldcc = T.ldc[c];
-   const int pn = T.n[p], pldl = T.ldl[p], pldc = T.ldc[p];
+   const int pldl = T.ldl[p], pldc = T.ldc[p];
    double* PL = T.L + T.loff[p];
    double* PC = T.C + T.coff[p];
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const int jend = min(k, w.y + 32);
    for (int j = w.y + warp; j < jend; j += 8) {
       const int rj = cm[j];
+      if ((rj < pn) != (part == 0)) continue;
       const double* s = src + (size_t)j * ldcc;
       double* dcol = (rj < pn) ? PL + (size_t)rj * pldl : PC + (size_t)(rj - pn) * pldc - pn;
-      for (int i = j + lane; i < k; i += 32) dcol[cm[i]] += s[i];
+      int i = j + lane;
+      for (; i + 96 < k; i += 128) {      // 4 independent read-modify-writes in flight per lane
+         const int r0 = cm[i], r1 = cm[i + 32], r2 = cm[i + 64], r3 = cm[i + 96];
+         const double v0 = s[i], v1 = s[i + 32], v2 = s[i + 64], v3 = s[i + 96];
+         const double d0 = dcol[r0], d1 = dcol[r1], d2 = dcol[r2], d3 = dcol[r3];
+         dcol[r0] = d0 + v0; dcol[r1] = d1 + v1; dcol[r2] = d2 + v2; dcol[r3] = d3 + v3;
+      }
+      for (; i < k; i += 32) dcol[cm[i]] += s[i];
    }
 }
 

@@ -780,12 +780,16 @@ static __global__ void __launch_bounds__(256) k_assemble_delays(DevTree T, const
 
 // Extend-add (delay aware variant of k_assemble): parent-local row of child contribution
 // row i is cmap[i] (+ ndelay_in of the parent if it is not a fully-summed row).
-static __global__ void __launch_bounds__(256) k_assemble_indef(DevTree T, const int2* __restrict__ work) {
+static __global__ void __launch_bounds__(256) k_assemble_indef(DevTree T, const int2* __restrict__ work, int part) {
    const int2 w = work[blockIdx.x];
    const int c = w.x;
    const int p = T.parent[c];
    const int k = T.m[c] - T.n[c];
    const int* cm = T.cmap + T.cmapoff[c];
+   {
+      const int je = min(k, w.y + 32);
+      if (part == 0 ? (cm[w.y] >= T.ncol0[p]) : (cm[je - 1] < T.ncol0[p])) return;
+   }
    const double* src = T.C + T.coff[c];
    const int ldcc = T.ldc[c];
    const int pncol0 = T.ncol0[p], pnd = T.n[p] - pncol0, pldl = T.ldl[p], pldc = T.ldc[p];
@@ -795,6 +799,7 @@ static __global__ void __launch_bounds__(256) k_assemble_indef(DevTree T, const 
    const int jend = min(k, w.y + 32);
    for (int j = w.y + warp; j < jend; j += 8) {
       const int rj = cm[j];
+      if ((rj < pncol0) != (part == 0)) continue;
       const double* s = src + (size_t)j * ldcc;
       if (rj < pncol0) {
          double* dcol = PL + (size_t)rj * pldl;
