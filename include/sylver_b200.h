@@ -273,6 +273,12 @@ int sylver_b200_comm_world(void);
 /* Planning-only communicator (no NCCL object): lets host code inspect what rank `rank` of
  * `world` would do; numeric calls with it fail. */
 void sylver_b200_comm_set_virtual(int rank, int world);
+/* Thread-per-rank communicator: `world` threads of ONE process, all on the current device,
+ * each call this once (same fabric_id) before factorizing its share and
+ * sylver_b200_comm_finalize() before exiting.  The multi-rank schedule (tree partition,
+ * contribution/delay hand-over, distributed fronts) then runs over device-to-device copies
+ * instead of NCCL -- the transport the single-GPU test box uses.  Thread local. */
+int sylver_b200_comm_init_local(int rank, int world, int fabric_id);
 /* owner[f] (0-based rank) of every front for `world` GPUs; returns the number of fronts.
  * Replaces the reference's prune_tree / find_subtree_partition
  * (src/spldlt_analyse_mod.F90:949-1141,1435-1656): proportional mapping by flops. */

@@ -82,6 +82,7 @@ EXPORTS = [
     "sylver_b200_numeric_tree_get_front", "sylver_b200_numeric_tree_get_front_indef",
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
+    "sylver_b200_comm_init_local",
     "sylver_b200_partition", "sylver_b200_plan_exchanges",
 ]
 
@@ -149,6 +150,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_comm_unique_id.argtypes = [vp]
     L.sylver_b200_comm_init.argtypes = [C.c_int, C.c_int, vp]
     L.sylver_b200_comm_set_virtual.argtypes = [C.c_int, C.c_int]
+    L.sylver_b200_comm_init_local.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sylver_b200_partition.argtypes = [vp, C.c_int, vp]
     L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
@@ -201,6 +203,43 @@ def comm_init_from_torch(dist, device_index: int) -> None:
     idbuf = (C.c_ubyte * 128).from_buffer_copy(raw)
     if L.sylver_b200_comm_init(rank, world, idbuf) != 0:
         raise RuntimeError("sylver_b200_comm_init failed")
+
+
+_fabric_seq = [0]
+
+
+def run_local_ranks(world: int, fn, timeout: float = 600.0):
+    """Run ``fn(rank, world)`` on `world` threads of this process, each joined to a fresh
+    in-process communicator (sylver_b200_comm_init_local): the multi-rank factorization and
+    solve on ONE device.  Returns the list of results; re-raises the first exception."""
+    import threading
+    L = lib()
+    _fabric_seq[0] += 1
+    fid = _fabric_seq[0]
+    out, err = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            if L.sylver_b200_comm_init_local(r, world, fid) != 0:
+                raise RuntimeError("sylver_b200_comm_init_local failed")
+            try:
+                out[r] = fn(r, world)
+            finally:
+                L.sylver_b200_comm_finalize()
+        except BaseException as e:      # noqa: BLE001 - reported to the caller below
+            err[r] = e
+
+    ts = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout)
+        if t.is_alive():
+            raise TimeoutError("a local rank did not finish (deadlocked exchange?)")
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 def partition(solver: "Solver", world: int) -> np.ndarray:

@@ -392,6 +392,7 @@ int sylver_b200_comm_init(int rank, int world, void const* id128) {
    return comm_init(rank, world, id128);
 }
 void sylver_b200_comm_set_virtual(int rank, int world) { comm_set_virtual(rank, world); }
+int sylver_b200_comm_init_local(int rank, int world, int fabric_id) { return comm_init_local(rank, world, fabric_id); }
 void sylver_b200_comm_finalize(void) { comm_finalize(); }
 int sylver_b200_comm_rank(void) { return comm().rank; }
 int sylver_b200_comm_world(void) { return comm().world; }

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "engine_impl.hpp"
 #include "kernels_solve.cuh"
@@ -47,6 +48,7 @@ SymbolicTree::~SymbolicTree() {
    cudaFree(d_rlist); cudaFree(d_rptr); cudaFree(d_nlist); cudaFree(d_anode); cudaFree(d_nrow);
    cudaFree(d_ncol); cudaFree(d_parent); cudaFree(d_nchild); cudaFree(d_cmap); cudaFree(d_cmapoff);
    cudaFree(d_level_nodes); cudaFree(d_nptr);
+   cudaFree(d_fchild); cudaFree(d_pinvoff); cudaFree(d_pinv);
 }
 
 // Host-only copies needed again at upload time
@@ -56,9 +58,15 @@ struct SymbolicExtra {
    std::vector<int> anode;    // owning front of each entry
    std::vector<long> nptr1;   // 1-based nptr as given
 };
-static std::map<const SymbolicTree*, SymbolicExtra>& extras() {
+// rank threads of a local fabric analyse and factorize concurrently: the registry is locked
+static std::mutex g_extras_mu;
+static std::map<const SymbolicTree*, SymbolicExtra>& extras_map() {
    static std::map<const SymbolicTree*, SymbolicExtra> m;
    return m;
+}
+static SymbolicExtra& extras_of(const SymbolicTree* st) {
+   std::lock_guard<std::mutex> lk(g_extras_mu);
+   return extras_map()[st];      // std::map references stay valid across other insertions
 }
 
 SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int* sparent,
@@ -114,6 +122,40 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
          st->cmap[st->cmapoff[c] + i] = q;
       }
    }
+   // fused extend-add: the two children with the largest generated elements of every front
+   st->fchild.assign(2 * (size_t)nnodes, -1);
+   st->pinvoff.assign(2 * (size_t)nnodes, 0);
+   {
+      const char* fe = getenv("SYLVER_B200_FUSE_ASM");
+      const bool fuse = !(fe && fe[0] == '0');
+      for (int p = 0; fuse && p < nnodes; ++p) {
+         const int kp = st->nrow[p] - st->ncol[p];
+         if (kp == 0) continue;
+         int best[2] = {-1, -1};
+         for (int ci = st->child_ptr[p]; ci < st->child_ptr[p + 1]; ++ci) {
+            const int c = st->child_list[ci];
+            const int k = st->nrow[c] - st->ncol[c];
+            if (k < 16) continue;      // tiny blocks: the scatter kernel is as good
+            if (best[0] < 0 || k > st->nrow[best[0]] - st->ncol[best[0]]) { best[1] = best[0]; best[0] = c; }
+            else if (best[1] < 0 || k > st->nrow[best[1]] - st->ncol[best[1]]) best[1] = c;
+         }
+         for (int s = 0; s < 2; ++s) {
+            const int c = best[s];
+            if (c < 0) continue;
+            const int k = st->nrow[c] - st->ncol[c];
+            const int* cm = &st->cmap[st->cmapoff[c]];
+            // rows of the child's block that land in the parent's contribution block
+            int first = 0;
+            while (first < k && cm[first] < st->ncol[p]) ++first;
+            if (first == k) continue;
+            st->fchild[2 * (size_t)p + s] = c;
+            st->pinvoff[2 * (size_t)p + s] = (long)st->pinv.size();
+            st->pinv.resize(st->pinv.size() + kp, -1);
+            int* pv = st->pinv.data() + st->pinvoff[2 * (size_t)p + s];
+            for (int i = first; i < k; ++i) pv[cm[i] - st->ncol[p]] = i;
+         }
+      }
+   }
    // levels = height above the leaves
    for (int i = 0; i < nnodes; ++i) {
       const int p = st->parent[i];
@@ -134,7 +176,7 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
                           [&](int a, int b) { return st->ncol[a] > st->ncol[b]; });
    }
    // A -> front map
-   SymbolicExtra& ex = extras()[st];
+   SymbolicExtra& ex = extras_of(st);
    ex.rptr1.assign(rptr, rptr + nnodes + 1);
    ex.nptr1.assign(nptr, nptr + nnodes + 1);
    st->nent = nnodes ? nptr[nnodes] - 1 : 0;
@@ -151,7 +193,7 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
 
 static void symbolic_tree_upload(SymbolicTree* st) {
    if (st->on_device) return;
-   SymbolicExtra& ex = extras()[st];
+   SymbolicExtra& ex = extras_of(st);
    CU_TRY(cudaGetDevice(&st->device));
    st->d_rlist = dev_upload(st->rlist);
    st->d_rptr = dev_upload(ex.rptr1);
@@ -165,12 +207,18 @@ static void symbolic_tree_upload(SymbolicTree* st) {
    st->d_cmap = dev_upload(st->cmap);
    st->d_cmapoff = dev_upload(st->cmapoff);
    st->d_level_nodes = dev_upload(st->level_nodes);
+   st->d_fchild = dev_upload(st->fchild);
+   st->d_pinvoff = dev_upload(st->pinvoff);
+   st->d_pinv = dev_upload(st->pinv);
    st->on_device = true;
    ex.nlist.clear(); ex.nlist.shrink_to_fit();
    ex.anode.clear(); ex.anode.shrink_to_fit();
 }
 
-void symbolic_tree_forget(const SymbolicTree* st) { extras().erase(st); }
+void symbolic_tree_forget(const SymbolicTree* st) {
+   std::lock_guard<std::mutex> lk(g_extras_mu);
+   extras_map().erase(st);
+}
 
 bool numeric_tree_posdef(const NumericTree* nt) { return nt->posdef; }
 
@@ -228,6 +276,20 @@ void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int r
       }
 }
 
+// owned fronts per level (order of st->level_nodes preserved: ncol descending)
+void plan_owned_levels(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   nt->lvl_ptr.assign(st->nlevels + 1, 0);
+   nt->lvl_nodes.clear();
+   for (int l = 0; l < st->nlevels; ++l) {
+      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i)
+         if (nt->owner[st->level_nodes[i]] == nt->rank) nt->lvl_nodes.push_back(st->level_nodes[i]);
+      nt->lvl_ptr[l + 1] = (int)nt->lvl_nodes.size();
+   }
+   if (nt->d_lvl_nodes) cudaFree(nt->d_lvl_nodes);
+   nt->d_lvl_nodes = dev_upload(nt->lvl_nodes);
+}
+
 static void build_posdef_plan(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
@@ -247,14 +309,7 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->L_doubles = loff + 4;
    plan_contrib_arena(nt);
    plan_exchanges(*st, nt->owner, me, nt->sends, nt->recvs);
-   // owned fronts per level (order of st->level_nodes preserved: ncol descending)
-   nt->lvl_ptr.assign(st->nlevels + 1, 0);
-   nt->lvl_nodes.clear();
-   for (int l = 0; l < st->nlevels; ++l) {
-      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i)
-         if (nt->owner[st->level_nodes[i]] == me) nt->lvl_nodes.push_back(st->level_nodes[i]);
-      nt->lvl_ptr[l + 1] = (int)nt->lvl_nodes.size();
-   }
+   plan_owned_levels(nt);
 
    // work lists
    std::vector<int> prefix;
@@ -382,7 +437,6 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->W_doubles = wmax;
    nt->d_prefix = dev_upload(prefix);
    nt->d_asm_work = dev_upload(asmw);
-   nt->d_lvl_nodes = dev_upload(nt->lvl_nodes);
 }
 
 void upload_geometry(NumericTree* nt) {
@@ -395,6 +449,7 @@ void upload_geometry(NumericTree* nt) {
    T.loff = nt->d_loff; T.coff = nt->d_coff; T.cmapoff = st->d_cmapoff;
    T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
    T.L = nt->d_L; T.C = nt->d_C;
+   T.fchild = st->d_fchild; T.pinvoff = st->d_pinvoff; T.pinv = st->d_pinv;
 }
 
 // Contribution blocks (factorization) or solve work vectors whose parent front lives on another
@@ -525,6 +580,8 @@ static void issue_posdef(NumericTree* nt) {
 
 static void set_kernel_attributes() {
    static bool done = false;
+   static std::mutex mu;
+   std::lock_guard<std::mutex> lk(mu);
    if (done) return;
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<128>::SMEM));
@@ -601,7 +658,6 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       nt->nb = 128;
       nt->rank = comm().rank;
       nt->world = comm().world;
-      if (nt->world > 1 && !posdef) throw CudaFailure{-98};   // multi-GPU APTP: not in this round
       if (g_have_user_stream) {
          nt->stream = g_user_stream;
          nt->own_stream = false;
@@ -776,7 +832,12 @@ static void ensure_solve_workspace(NumericTree* nt) {
    nt->d_xwoff = dev_upload(nt->xwoff);
    if (!nt->d_child_ptr) nt->d_child_ptr = dev_upload(st->child_ptr);
    if (!nt->d_child_list) nt->d_child_list = dev_upload(st->child_list);
-   if (nt->world > 1 && !nt->d_all_nodes) {
+   if (nt->world > 1 && !nt->posdef && !nt->d_xbuf) {
+      // replicated-x delta exchange (k_delta_pack): previous x + (value, changed) pairs
+      nt->xbuf_cap = 3 * (size_t)std::max(st->n, 1);
+      CU_TRY(cudaMalloc(&nt->d_xbuf, nt->xbuf_cap * sizeof(double)));
+   }
+   if (nt->world > 1 && nt->posdef && !nt->d_all_nodes) {
       // per-level packing offsets of every front's own variables (solve broadcasts)
       std::vector<int> off(st->nnodes);
       size_t cap = 1;
@@ -831,6 +892,17 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
       for (int r = 0; r < nrhs; ++r) {
          a.x = dx + (size_t)r * ldx;
          const bool multi = nt->world > 1;
+         // multi-rank indefinite: publish what each rank changed after every level (see k_delta_pack)
+         const bool delta = multi && !nt->posdef;
+         const int nn = st->n, gn = (nn + 255) / 256;
+         double* xprev = nt->d_xbuf;
+         double* xd = delta ? nt->d_xbuf + nn : nullptr;
+         auto sync_x = [&]() {
+            k_delta_pack<<<gn, 256, 0, nt->stream>>>(nn, a.x, xprev, xd);
+            if (comm_allreduce_sum(xd, 2 * (size_t)nn, nt->stream)) throw CudaFailure{-52};
+            k_delta_unpack<<<gn, 256, 0, nt->stream>>>(nn, a.x, xprev, xd);
+         };
+         if (delta) CU_TRY(cudaMemcpyAsync(xprev, a.x, nn * sizeof(double), cudaMemcpyDeviceToDevice, nt->stream));
          const int* lptr = multi ? nt->lvl_ptr.data() : st->level_ptr.data();
          const int* d_nodes = multi ? nt->d_lvl_nodes : st->d_level_nodes;
          if (do_fwd) {
@@ -839,20 +911,25 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
                if (count > 0) k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
                // update vectors of fronts whose parent lives on another GPU (rows >= n of xw)
                if (multi) issue_exchange(nt, l, nt->d_xw, nt->xwoff, &nt->n);
+               if (delta) sync_x();
             }
-            if (multi && !do_bwd) {
+            if (multi && !delta && !do_bwd) {
                // forward solve only: merge the per-rank pieces into one replicated vector
                k_zero_unowned<<<st->nnodes, 256, 0, nt->stream>>>(st->nnodes, nt->d_owner, nt->rank, st->d_rlist,
                                                                    st->d_rptr, st->d_ncol, a.x);
                if (comm_allreduce_sum(a.x, (size_t)st->n, nt->stream)) throw CudaFailure{-52};
             }
          }
-         if (do_diag) k_solve_diag<<<(st->nnodes + 7) / 8, 256, 0, nt->stream>>>(a, st->nnodes);
+         if (do_diag) {
+            k_solve_diag<<<(st->nnodes + 7) / 8, 256, 0, nt->stream>>>(a, st->nnodes, multi ? nt->d_owner : nullptr, nt->rank);
+            if (delta) sync_x();
+         }
          if (do_bwd)
             for (int l = st->nlevels - 1; l >= 0; --l) {
                const int first = lptr[l], count = lptr[l + 1] - first;
                if (count > 0) k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
-               if (multi) {
+               if (delta) sync_x();
+               if (multi && !delta) {
                   // broadcast the entries solved at this level: pack (zeros for fronts of other
                   // ranks), all-reduce, unpack into the replicated x
                   const int af = st->level_ptr[l], ac = st->level_ptr[l + 1] - af;

@@ -26,6 +26,11 @@ struct SymbolicTree {
    std::vector<long> cmapoff;                // per node, offset into cmap
    std::vector<int> cmap;                    // child contribution row -> parent local row (0-based)
    std::vector<int> level_ptr, level_nodes;  // fronts grouped by level (height), ncol descending
+   // extend-add fused into the contribution epilogue: per front up to two children whose
+   // blocks are gathered (largest first), and parent-contribution-row -> child-row maps
+   std::vector<int> fchild;                  // [2*nnodes], -1 = none
+   std::vector<long> pinvoff;                // [2*nnodes]
+   std::vector<int> pinv;
    int nlevels = 0;
    // ---- device resident static data ----
    int* d_rlist = nullptr;
@@ -40,6 +45,9 @@ struct SymbolicTree {
    long* d_cmapoff = nullptr;
    int* d_level_nodes = nullptr;
    long* d_nptr = nullptr;       // 1-based values as given (nnodes+1)
+   int* d_fchild = nullptr;
+   long* d_pinvoff = nullptr;
+   int* d_pinv = nullptr;
    bool on_device = false;
    int device = 0;
 

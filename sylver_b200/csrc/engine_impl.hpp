@@ -220,6 +220,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats);
 void indef_setup(NumericTree* nt);
 void indef_destroy(NumericTree* nt);
 void plan_contrib_arena(NumericTree* nt);
+void plan_owned_levels(NumericTree* nt);
 void upload_geometry(NumericTree* nt);
 void load_values(NumericTree* nt, const double* aval, const double* scaling);
 

@@ -31,10 +31,16 @@ static __global__ void k_set_geometry(const GeoUpd* __restrict__ u, int cnt, int
    loff[g.f] = g.loff; woff[g.f] = g.woff; doff[g.f] = g.doff; permoff[g.f] = g.permoff;
 }
 
-static __global__ void k_copy_nelim(const int* __restrict__ fronts, const int* __restrict__ lvl_nelim, int cnt,
-                                    int* __restrict__ nelim_all) {
+// Publishes the eliminated-column counts of ALL fronts of a level (after the all-reduce of a
+// multi-rank run they include the fronts of other ranks): the per-front array the solves
+// read, and state[f].nelim, which k_assemble_delays reads for a remote child's ghost.
+static __global__ void k_publish_nelim(const int* __restrict__ fronts, const int* __restrict__ lvl_nelim, int cnt,
+                                       int* __restrict__ nelim_all, FrontState* __restrict__ state) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < cnt) nelim_all[fronts[i]] = lvl_nelim[i];
+   if (i >= cnt) return;
+   const int f = fronts[i];
+   nelim_all[f] = lvl_nelim[i];
+   state[f].nelim = lvl_nelim[i];
 }
 
 // ---- factor arena: bump allocation in chunks, offsets relative to chunk 0 ----
@@ -71,10 +77,15 @@ void indef_setup(NumericTree* nt) {
    nt->m.assign(N, 0); nt->n.assign(N, 0); nt->ldl.assign(N, 0); nt->loff.assign(N, 0);
    nt->woff.assign(N, 0); nt->doff.assign(N, 0); nt->permoff.assign(N, 0);
    nt->nelim.assign(N, 0);
+   partition_tree(*st, nt->world, nt->owner);
    plan_contrib_arena(nt);
+   plan_exchanges(*st, nt->owner, nt->rank, nt->sends, nt->recvs);
+   plan_owned_levels(nt);
+   if (nt->world > 1) nt->d_owner = dev_upload(nt->owner);
    CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
    size_t est = 0;
    for (int f = 0; f < N; ++f) {
+      if (nt->owner[f] != nt->rank) continue;
       const size_t ldl = round_up(st->nrow[f], 4);
       est += ((ldl * st->ncol[f] + 2 * (size_t)st->ncol[f] + (st->ncol[f] + 1) / 2 + 15) & ~(size_t)15);
    }
@@ -104,6 +115,7 @@ void indef_setup(NumericTree* nt) {
    T.ncol0 = nt->d_ncol0; T.woff = nt->d_woff; T.doff = nt->d_doff; T.permoff = nt->d_permoff;
    T.W = nullptr; T.D = nt->chunks[0].ptr; T.perm = reinterpret_cast<int*>(nt->chunks[0].ptr);
    T.state = nt->d_state;
+   T.fchild = st->d_fchild; T.pinvoff = st->d_pinvoff; T.pinv = st->d_pinv;
    for (int c = 0; c < KC_COUNT; ++c) nt->prof_flops[c] = 0;
 }
 
@@ -134,12 +146,91 @@ struct Packer {
 };
 }  // namespace
 
+// (re)allocates the per-level upload buffer pair and copies `pk` to the device
+static void upload_level_buffer(NumericTree* nt, const Packer& pk) {
+   cudaStream_t s = nt->stream;
+   if (pk.buf.size() > nt->lvl_cap) {
+      CU_TRY(cudaStreamSynchronize(s));
+      if (nt->h_lvl) CU_TRY(cudaFreeHost(nt->h_lvl));
+      char* dl = static_cast<char*>(nt->d_lvl);
+      size_t cap = nt->lvl_cap;
+      ensure_cap(dl, cap, pk.buf.size());
+      nt->d_lvl = dl;
+      nt->lvl_cap = cap;
+      CU_TRY(cudaMallocHost(&nt->h_lvl, cap));
+   }
+   if (pk.buf.empty()) return;
+   memcpy(nt->h_lvl, pk.buf.data(), pk.buf.size());
+   CU_TRY(cudaMemcpyAsync(nt->d_lvl, nt->h_lvl, pk.buf.size(), cudaMemcpyHostToDevice, s));
+}
+
+// Hand-over of one level's results to the ranks that own the parents (multi-rank runs):
+// contribution blocks as in the positive definite path, plus -- the part delayed pivots add,
+// SURVEY.md 8e "if indefinite with delays" -- the failed columns [nelim, n) of the child's L
+// panel and their slice of the pivot permutation.  The receiver keeps them in a "ghost" of
+// the child (only those columns are backed by memory) so that k_assemble_delays reads a
+// remote child exactly like a local one.  Both sides know every nelim (all-reduced per
+// level), so message sizes need no handshake.
+static void exchange_level_indef(NumericTree* nt, int l) {
+   SymbolicTree* st = nt->st;
+   cudaStream_t s = nt->stream;
+   const auto& sd = nt->sends[l];
+   const auto& rv = nt->recvs[l];
+   if (sd.empty() && rv.empty()) return;
+   std::vector<GeoUpd> ghosts;
+   for (const Xfer& x : rv) {
+      const int c = x.f;
+      const int nd = nt->n[c] - nt->nelim[c];
+      if (nd <= 0) continue;
+      const size_t cols = (size_t)nd * nt->ldl[c];
+      const long off = arena_alloc(nt, cols + (nd + 1) / 2);
+      nt->loff[c] = off - (long)nt->nelim[c] * nt->ldl[c];
+      nt->permoff[c] = 2 * (off + (long)cols) - nt->nelim[c];
+      ghosts.push_back(GeoUpd{c, nt->m[c], nt->n[c], nt->ldl[c], nt->loff[c], 0, 0, nt->permoff[c]});
+   }
+   if (!ghosts.empty()) {
+      Packer pk;
+      pk.put(ghosts);
+      upload_level_buffer(nt, pk);
+      k_set_geometry<<<((int)ghosts.size() + 255) / 256, 256, 0, s>>>(static_cast<const GeoUpd*>(nt->d_lvl), (int)ghosts.size(),
+                                                                     nt->d_m, nt->d_n, nt->d_ldl, nt->d_loff, nt->d_woff,
+                                                                     nt->d_doff, nt->d_permoff);
+   }
+   double* Lb = nt->chunks[0].ptr;
+   int* Pb = reinterpret_cast<int*>(nt->chunks[0].ptr);
+   int rc = comm_group_start();
+   for (const Xfer& x : sd) {
+      const int f = x.f;
+      const size_t k = (size_t)(st->nrow[f] - st->ncol[f]);
+      rc |= comm_send(nt->d_C + nt->coff[f], k * nt->ldc[f], x.peer, s);
+      const int ne = nt->nelim[f], nd = nt->n[f] - ne;
+      if (nd > 0) {
+         rc |= comm_send(Lb + nt->loff[f] + (long)ne * nt->ldl[f], (size_t)nd * nt->ldl[f], x.peer, s);
+         rc |= comm_send_int(Pb + nt->permoff[f] + ne, (size_t)nd, x.peer, s);
+      }
+   }
+   for (const Xfer& x : rv) {
+      const int c = x.f;
+      const size_t k = (size_t)(st->nrow[c] - st->ncol[c]);
+      rc |= comm_recv(nt->d_C + nt->coff[c], k * nt->ldc[c], x.peer, s);
+      const int ne = nt->nelim[c], nd = nt->n[c] - ne;
+      if (nd > 0) {
+         rc |= comm_recv(Lb + nt->loff[c] + (long)ne * nt->ldl[c], (size_t)nd * nt->ldl[c], x.peer, s);
+         rc |= comm_recv_int(Pb + nt->permoff[c] + ne, (size_t)nd, x.peer, s);
+      }
+   }
+   rc |= comm_group_end();
+   if (rc) throw CudaFailure{-52};
+}
+
 void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
    cudaStream_t s = nt->stream;
    const double u = nt->opt.u, small = nt->opt.small;
    const bool tpp_everywhere = (nt->opt.failed_pivot_method != 2) || (nt->opt.pivot_method == 3);
+   const bool multi = nt->world > 1;
+   const int me = nt->rank;
    long launches = 0;
    for (auto& c : nt->chunks) c.used = 0;
    if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
@@ -150,35 +241,43 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    CU_TRY(cudaEventRecord(nt->ev0, s));
    CU_TRY(cudaMemsetAsync(nt->d_stats, 0, 8 * sizeof(int), s));
    int maxfront = 0;
-   std::vector<int> order;
+   std::vector<int> order, slot;
    for (int l = 0; l < st->nlevels; ++l) {
-      const int first = st->level_ptr[l], cnt = st->level_ptr[l + 1] - first;
-      if (cnt == 0) continue;
-      // ---- geometry of the level (children are complete: their nelim is known) ----
-      order.assign(st->level_nodes.begin() + first, st->level_nodes.begin() + first + cnt);
-      std::vector<GeoUpd> geo(cnt);
+      const int gfirst = st->level_ptr[l], gcnt = st->level_ptr[l + 1] - gfirst;
+      if (gcnt == 0) continue;
+      // ---- geometry of the level (children are complete: their nelim is known on every rank).
+      // Sizes are computed for all fronts of the level, memory only for the fronts of this rank.
+      order.clear();
+      std::vector<GeoUpd> geo;
       std::vector<int2> delay_work;
       size_t wtotal = 0;
       std::vector<std::pair<size_t, size_t>> runs;      // arena ranges to clear (bytes offsets from chunk 0)
       int max_children = 0, maxn = 0, maxk = 0;
       long max_ent = 0;
-      for (int i = 0; i < cnt; ++i) {
-         const int f = order[i];
+      for (int i = 0; i < gcnt; ++i) {
+         const int f = st->level_nodes[gfirst + i];
+         const bool mine = nt->owner[f] == me;
          int nd = 0;
          for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
             const int c = st->child_list[ci];
             const int d = nt->n[c] - nt->nelim[c];
-            if (d > 0) delay_work.push_back(make_int2(c, st->ncol[f] + nd));
+            if (d > 0 && mine) delay_work.push_back(make_int2(c, st->ncol[f] + nd));
             nd += d;
          }
-         max_children = std::max(max_children, st->nchild[f]);
-         if (st->nchild[f] > 0) maxk = std::max(maxk, st->nrow[f] - st->ncol[f]);
-         max_ent = std::max(max_ent, st->aent[f]);
          const int m = st->nrow[f] + nd, n = st->ncol[f] + nd;
          const int ldl = round_up(m, 4);
          nt->m[f] = m; nt->n[f] = n; nt->ldl[f] = ldl;
-         maxn = std::max(maxn, n);
          maxfront = std::max(maxfront, m);
+         if (!mine) {
+            nt->loff[f] = nt->woff[f] = nt->doff[f] = nt->permoff[f] = 0;
+            geo.push_back(GeoUpd{f, m, n, ldl, 0, 0, 0, 0});
+            continue;
+         }
+         order.push_back(f);
+         max_children = std::max(max_children, st->nchild[f]);
+         if (st->nchild[f] > 0) maxk = std::max(maxk, st->nrow[f] - st->ncol[f]);
+         max_ent = std::max(max_ent, st->aent[f]);
+         maxn = std::max(maxn, n);
          const size_t panel = (size_t)ldl * n;
          const size_t block = panel + 2 * (size_t)n + (n + 1) / 2;
          const long off = arena_alloc(nt, block);
@@ -193,10 +292,20 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          else
             runs.emplace_back((size_t)off * sizeof(double), bytes);
       }
+      const int cnt = (int)order.size();
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nt->n[a] > nt->n[b]; });
+      slot.resize(cnt);
+      {
+         // position of every owned front in the level's global list (where its nelim is published)
+         std::vector<std::pair<int, int>> pos(gcnt);
+         for (int i = 0; i < gcnt; ++i) pos[i] = {st->level_nodes[gfirst + i], i};
+         std::sort(pos.begin(), pos.end());
+         for (int i = 0; i < cnt; ++i)
+            slot[i] = std::lower_bound(pos.begin(), pos.end(), std::make_pair(order[i], 0))->second;
+      }
       for (int i = 0; i < cnt; ++i) {
          const int f = order[i];
-         geo[i] = GeoUpd{f, nt->m[f], nt->n[f], nt->ldl[f], nt->loff[f], nt->woff[f], nt->doff[f], nt->permoff[f]};
+         geo.push_back(GeoUpd{f, nt->m[f], nt->n[f], nt->ldl[f], nt->loff[f], nt->woff[f], nt->doff[f], nt->permoff[f]});
       }
       // work lists (prefix sums are nested: step s uses the first cnt_s fronts of `order`)
       std::vector<int> row_prefix(cnt + 1), upd_prefix(cnt + 1), con_prefix(cnt + 1);
@@ -233,23 +342,13 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       Packer pk;
       const size_t o_geo = pk.put(geo), o_order = pk.put(order), o_row = pk.put(row_prefix),
                    o_upd = pk.put(upd_prefix), o_con = pk.put(con_prefix), o_asm = pk.put(asmw),
-                   o_del = pk.put(delay_work);
+                   o_del = pk.put(delay_work), o_slot = pk.put(slot);
       // ---- device buffers for the level ----
       {
-         char* dl = static_cast<char*>(nt->d_lvl);
-         if (pk.buf.size() > nt->lvl_cap) {
-            CU_TRY(cudaStreamSynchronize(s));
-            if (nt->h_lvl) CU_TRY(cudaFreeHost(nt->h_lvl));
-            size_t cap = nt->lvl_cap;
-            ensure_cap(dl, cap, pk.buf.size());
-            nt->d_lvl = dl;
-            nt->lvl_cap = cap;
-            CU_TRY(cudaMallocHost(&nt->h_lvl, cap));
-         }
-         if ((size_t)cnt > nt->lvl_out_cap) {
+         if ((size_t)gcnt > nt->lvl_out_cap) {
             CU_TRY(cudaStreamSynchronize(s));
             if (nt->h_lvl_out) CU_TRY(cudaFreeHost(nt->h_lvl_out));
-            ensure_cap(nt->d_lvl_out, nt->lvl_out_cap, (size_t)cnt);
+            ensure_cap(nt->d_lvl_out, nt->lvl_out_cap, (size_t)gcnt);
             CU_TRY(cudaMallocHost(&nt->h_lvl_out, nt->lvl_out_cap * sizeof(int)));
          }
          if ((size_t)cnt > nt->diag_cap) {
@@ -266,8 +365,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       }
       nt->T.W = nt->d_W;
       const DevTree& T = nt->T;
-      memcpy(nt->h_lvl, pk.buf.data(), pk.buf.size());
-      CU_TRY(cudaMemcpyAsync(nt->d_lvl, nt->h_lvl, pk.buf.size(), cudaMemcpyHostToDevice, s));
+      upload_level_buffer(nt, pk);
       char* dl = static_cast<char*>(nt->d_lvl);
       const GeoUpd* d_geo = reinterpret_cast<const GeoUpd*>(dl + o_geo);
       const int* d_fr = reinterpret_cast<const int*>(dl + o_order);
@@ -276,77 +374,87 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       const int* d_con = reinterpret_cast<const int*>(dl + o_con);
       const int2* d_asm = reinterpret_cast<const int2*>(dl + o_asm);
       const int2* d_del = reinterpret_cast<const int2*>(dl + o_del);
+      const int* d_slot = reinterpret_cast<const int*>(dl + o_slot);
       DiagScratch* d_diag = static_cast<DiagScratch*>(nt->d_diag);
-      k_set_geometry<<<(cnt + 255) / 256, 256, 0, s>>>(d_geo, cnt, nt->d_m, nt->d_n, nt->d_ldl, nt->d_loff, nt->d_woff,
-                                                       nt->d_doff, nt->d_permoff);
+      k_set_geometry<<<((int)geo.size() + 255) / 256, 256, 0, s>>>(d_geo, (int)geo.size(), nt->d_m, nt->d_n, nt->d_ldl,
+                                                                   nt->d_loff, nt->d_woff, nt->d_doff, nt->d_permoff);
+      if (multi) CU_TRY(cudaMemsetAsync(nt->d_lvl_out, 0, gcnt * sizeof(int), s));
       for (auto& r : runs)
          CU_TRY(cudaMemsetAsync(reinterpret_cast<char*>(nt->chunks[0].ptr) + r.first, 0, r.second, s));
       launches += 1 + (long)runs.size();
-      // ---- assembly: A entries, children's generated elements, delayed columns ----
-      {
-         ProfScope ps(nt, KC_SCATTER);
-         k_init_front<<<cnt, 256, 0, s>>>(T, d_fr, st->d_rlist, st->d_rptr);
-         const int gy = (int)std::min<long>(std::max<long>((max_ent + 2047) / 2048, 1), 592);
-         k_scatter_a_fronts<<<dim3(cnt, gy), 256, 0, s>>>(T, d_fr, st->d_nptr, st->d_nlist, st->d_nrow, nt->d_aval, nt->d_scaling,
-                                                st->d_rlist, st->d_rptr);
-         launches += 2;
-      }
-      auto assemble = [&](int part) {
-         ProfScope ps(nt, KC_ASSEMBLE);
-         for (auto& w : asm_ranges) {
-            if (w.second == 0) continue;
-            k_assemble_indef<<<w.second, 256, 0, s>>>(T, d_asm + w.first, part);
+      if (cnt > 0) {
+         // ---- assembly: A entries, children's generated elements, delayed columns ----
+         {
+            ProfScope ps(nt, KC_SCATTER);
+            k_init_front<<<cnt, 256, 0, s>>>(T, d_fr, st->d_rlist, st->d_rptr);
+            const int gy = (int)std::min<long>(std::max<long>((max_ent + 2047) / 2048, 1), 592);
+            k_scatter_a_fronts<<<dim3(cnt, gy), 256, 0, s>>>(T, d_fr, st->d_nptr, st->d_nlist, st->d_nrow, nt->d_aval,
+                                                             nt->d_scaling, st->d_rlist, st->d_rptr);
+            launches += 2;
+         }
+         auto assemble = [&](int part) {
+            ProfScope ps(nt, KC_ASSEMBLE);
+            for (auto& w : asm_ranges) {
+               if (w.second == 0) continue;
+               k_assemble_indef<<<w.second, 256, 0, s>>>(T, d_asm + w.first, part);
+               ++launches;
+            }
+         };
+         assemble(0);
+         if (!delay_work.empty()) {
+            k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
             ++launches;
          }
-      };
-      assemble(0);
-      if (!delay_work.empty()) {
-         k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
-         ++launches;
-      }
-      // ---- APTP block columns ----
-      const int nsteps = (maxn + IB - 1) / IB;
-      int cnt_s = cnt;
-      for (int sidx = 0; sidx < nsteps; ++sidx) {
-         while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= sidx * IB) --cnt_s;
-         if (cnt_s == 0) break;
-         TileBatch rb{d_fr, d_row, cnt_s};
-         TileBatch ub{d_fr, d_upd, cnt_s};
-         {
-            ProfScope ps(nt, KC_POTRF);
-            k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
-            k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
-            k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
-            k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
-            launches += 4;
+         // ---- APTP block columns ----
+         const int nsteps = (maxn + IB - 1) / IB;
+         int cnt_s = cnt;
+         for (int sidx = 0; sidx < nsteps; ++sidx) {
+            while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= sidx * IB) --cnt_s;
+            if (cnt_s == 0) break;
+            TileBatch rb{d_fr, d_row, cnt_s};
+            TileBatch ub{d_fr, d_upd, cnt_s};
+            {
+               ProfScope ps(nt, KC_POTRF);
+               k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
+               k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
+               k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
+               k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
+               launches += 4;
+            }
+            {
+               ProfScope ps(nt, KC_UPDATE);
+               k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0);
+               ++launches;
+            }
          }
+         // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
          {
-            ProfScope ps(nt, KC_UPDATE);
-            k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0);
+            ProfScope ps(nt, KC_TRSM);
+            k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
             ++launches;
          }
-      }
-      // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
-      {
-         ProfScope ps(nt, KC_TRSM);
-         k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
+         if (con_prefix[cnt] > 0) {
+            TileBatch cb{d_fr, d_con, cnt};
+            ProfScope ps(nt, KC_CONTRIB);
+            k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0);
+            ++launches;
+         }
+         assemble(1);
+         k_front_stats<<<(cnt + 127) / 128, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out, d_slot);
          ++launches;
       }
-      if (con_prefix[cnt] > 0) {
-         TileBatch cb{d_fr, d_con, cnt};
-         ProfScope ps(nt, KC_CONTRIB);
-         k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0);
-         ++launches;
-      }
-      assemble(1);
-      k_front_stats<<<(cnt + 127) / 128, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out);
-      k_copy_nelim<<<(cnt + 255) / 256, 256, 0, s>>>(d_fr, nt->d_lvl_out, cnt, nt->d_nelim);
-      launches += 2;
-      CU_TRY(cudaMemcpyAsync(nt->h_lvl_out, nt->d_lvl_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+      // ---- every rank learns the eliminated counts of the whole level ----
+      if (multi && comm_allreduce_max_int(nt->d_lvl_out, (size_t)gcnt, s)) throw CudaFailure{-52};
+      k_publish_nelim<<<(gcnt + 255) / 256, 256, 0, s>>>(st->d_level_nodes + gfirst, nt->d_lvl_out, gcnt, nt->d_nelim,
+                                                         nt->d_state);
+      ++launches;
+      CU_TRY(cudaMemcpyAsync(nt->h_lvl_out, nt->d_lvl_out, gcnt * sizeof(int), cudaMemcpyDeviceToHost, s));
       CU_TRY(cudaStreamSynchronize(s));
       CU_TRY(cudaGetLastError());
-      for (int i = 0; i < cnt; ++i) nt->nelim[order[i]] = nt->h_lvl_out[i];
+      for (int i = 0; i < gcnt; ++i) nt->nelim[st->level_nodes[gfirst + i]] = nt->h_lvl_out[i];
+      if (multi) exchange_level_indef(nt, l);
    }
+   if (multi && comm_allreduce_sum_int(nt->d_stats, 8, s)) throw CudaFailure{-52};
    CU_TRY(cudaEventRecord(nt->ev1, s));
    int hs[8];
    CU_TRY(cudaMemcpyAsync(hs, nt->d_stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));

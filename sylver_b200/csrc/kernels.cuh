@@ -51,6 +51,14 @@ struct DevTree {
    double* D;
    int* perm;
    FrontState* state;
+   // ---- extend-add fused into the contribution-block epilogue (both paths) ----
+   // Up to two children per front (the ones with the largest generated elements) are not
+   // scattered into the parent's contribution block: the DMMA kernel that writes the block
+   // gathers them instead.  pinv + pinvoff[2f+s] maps parent contribution row q to the row of
+   // child fchild[2f+s]'s block that lands there (-1: none).  Static, built at analyse.
+   const int* fchild;    // [2*nnodes], -1 = unused slot; nullptr disables the fusion
+   const long* pinvoff;  // [2*nnodes]
+   const int* pinv;
 };
 
 // ---------------------------------------------------------------------------
@@ -383,6 +391,29 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const bool interior = (i0 + GT_BM <= m) && (j0 >= clo) && (j0 + GT_BN <= chi) && (i0 >= j0 + GT_BN - 1 || !lower) &&
                          (i0 >= rmin);
+   // Contribution block: fused extend-add.  The children's generated elements that the
+   // reference adds afterwards (assemble_contrib_block, src/kernels/assemble.hxx:343-517)
+   // are gathered here through the parent-row -> child-row maps, so the block is written
+   // once instead of written, re-read and re-written (8 + 8 B per entry instead of 8 + 24).
+   const double* fsrc[2] = {nullptr, nullptr};
+   const int* fmap[2] = {nullptr, nullptr};
+   int fld[2] = {0, 0};
+   int fir[2][4];
+   if (op == 1 && T.fchild) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+         const int fc = T.fchild[2 * f + s];
+         if (fc < 0) continue;
+         fsrc[s] = T.C + T.coff[fc];
+         fld[s] = T.ldc[fc];
+         fmap[s] = T.pinv + T.pinvoff[2 * f + s];
+#pragma unroll
+         for (int q = 0; q < 4; ++q) {
+            const int r = i0 + lane + 32 * q;
+            fir[s][q] = (r >= n && r < m) ? fmap[s][r - n] : -1;
+         }
+      }
+   }
 #pragma unroll 1
    for (int cq = 0; cq < 8; cq += 4) {
       double v[4][4], d[4][4];
@@ -396,6 +427,20 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
          gp[u] = dbase + (size_t)c * ldd + i0;
 #pragma unroll
          for (int q = 0; q < 4; ++q) v[u][q] = smem[(size_t)ct * GT_LDC + lane + 32 * q];
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+         if (!fsrc[s]) continue;
+#pragma unroll
+         for (int u = 0; u < 4; ++u) {
+            const int c = j0 + warp * 8 + cq + u;
+            const int ic = (c >= n && c < m) ? fmap[s][c - n] : -1;
+            if (ic < 0) continue;
+            const double* col = fsrc[s] + (size_t)ic * fld[s];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+               if (fir[s][q] >= ic) v[u][q] -= col[fir[s][q]];      // maps are increasing: row >= col
+         }
       }
       if (op == 0) {
 #pragma unroll
@@ -473,6 +518,8 @@ static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* 
    const int jend = min(k, w.y + 32);
    // cm is increasing: the chunk is skipped as a whole when it lies in the other part
    if (part == 0 ? (cm[w.y] >= pn) : (cm[jend - 1] < pn)) return;
+   // the contribution part of a fused child is gathered by the parent's DMMA epilogue
+   if (part == 1 && T.fchild && (T.fchild[2 * p] == c || T.fchild[2 * p + 1] == c)) return;
    const double* src = T.C + T.coff[c];
    const int ldcc = T.ldc[c];
    const int pldl = T.ldl[p], pldc = T.ldc[p];

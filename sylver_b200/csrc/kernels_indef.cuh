@@ -664,7 +664,7 @@ static __global__ void __launch_bounds__(TPP_THREADS) k_tpp(DevTree T, const int
 // stats: [0] num_delay [1] num_neg [2] num_two [3] num_zero [4] not_first_pass [5] not_second_pass
 // ---------------------------------------------------------------------------
 static __global__ void k_front_stats(DevTree T, const int* __restrict__ fronts, int cnt, int* __restrict__ stats,
-                                     int* __restrict__ nelim_out) {
+                                     int* __restrict__ nelim_out, const int* __restrict__ slot) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= cnt) return;
    const int f = fronts[i];
@@ -689,7 +689,7 @@ static __global__ void k_front_stats(DevTree T, const int* __restrict__ fronts, 
          j += 2;
       }
    }
-   nelim_out[i] = nelim;
+   nelim_out[slot[i]] = nelim;      // the front's position in the level's global list
    if (n - nelim) atomicAdd(&stats[0], n - nelim);
    if (neg) atomicAdd(&stats[1], neg);
    if (two) atomicAdd(&stats[2], two);
@@ -789,6 +789,7 @@ static __global__ void __launch_bounds__(256) k_assemble_indef(DevTree T, const 
    {
       const int je = min(k, w.y + 32);
       if (part == 0 ? (cm[w.y] >= T.ncol0[p]) : (cm[je - 1] < T.ncol0[p])) return;
+      if (part == 1 && T.fchild && (T.fchild[2 * p] == c || T.fchild[2 * p + 1] == c)) return;
    }
    const double* src = T.C + T.coff[c];
    const int ldcc = T.ldc[c];

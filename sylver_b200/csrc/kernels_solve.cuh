@@ -161,9 +161,11 @@ static __global__ void __launch_bounds__(256) k_zero_unowned(int nfronts, const 
 
 // D^-1 application of every front (indefinite only; ldlt_app_solve_diag,
 // spral/src/ssids/cpu/kernels/ldlt_app.cxx:2556-2578).  One warp per front.
-static __global__ void __launch_bounds__(256) k_solve_diag(SolveArgs a, int nfronts) {
+static __global__ void __launch_bounds__(256) k_solve_diag(SolveArgs a, int nfronts, const int* __restrict__ owner,
+                                                           int me) {
    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (f >= nfronts) return;
+   if (owner && owner[f] != me) return;      // multi-rank: D^-1 lives with the front's owner
    const int lane = threadIdx.x & 31;
    const int ne = a.nelim[f];
    const double* d = a.D + a.doff[f];
@@ -181,6 +183,27 @@ static __global__ void __launch_bounds__(256) k_solve_diag(SolveArgs a, int nfro
    }
    __syncwarp();
    for (int i = lane; i < ne; i += 32) a.x[perm[i] - 1] = xw[i];
+}
+
+// ---- multi-rank solve with delayed pivots: x is replicated, but the variables a front
+// touches are no longer its own contiguous range (delayed columns travel up the tree with
+// their variable), so after every level each rank publishes the entries it changed:
+// buf[i] = changed ? x[i] : 0, buf[n+i] = changed ? 1 : 0; all-reduce(sum); whoever changed an
+// entry (at most one rank: fronts of a level touch disjoint variables) wins.
+static __global__ void k_delta_pack(int n, const double* __restrict__ x, const double* __restrict__ xprev,
+                                    double* __restrict__ buf) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const bool ch = __double_as_longlong(x[i]) != __double_as_longlong(xprev[i]);
+   buf[i] = ch ? x[i] : 0.0;
+   buf[n + i] = ch ? 1.0 : 0.0;
+}
+static __global__ void k_delta_unpack(int n, double* __restrict__ x, double* __restrict__ xprev,
+                                      const double* __restrict__ buf) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   if (buf[n + i] != 0.0) x[i] = buf[i];
+   xprev[i] = x[i];
 }
 
 }  // namespace sylver_b200
