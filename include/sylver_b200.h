@@ -238,6 +238,10 @@ void *sylver_b200_akeep_tree(void *akeep);
  * wall time of the call, out[3]=kernel launches issued. */
 int sylver_b200_numeric_tree_timings(void const *tree, double *out4);
 void *sylver_b200_fkeep_tree(void *fkeep);
+/* Multi-GPU runs: out3[0] = fronts of the tree that are split over a rank group (block-column
+ * cyclic, panel broadcasts; SURVEY.md 8e "top of tree"), out3[1] = those this rank is a member
+ * of, out3[2] = contribution-block pieces this rank sends per factorization. */
+int sylver_b200_numeric_tree_split_info(void const *tree, int *out3);
 
 /* Per-kernel-class device time of the last factorization when the environment variable
  * SYLVER_B200_PROFILE=1 was set at tree creation (un-graphed issue, CUDA events around

@@ -75,7 +75,7 @@ EXPORTS = [
     "spldlt_tree_solve_fwd_dbl", "spldlt_tree_solve_bwd_dbl", "spldlt_tree_solve_diag_dbl",
     "spldlt_tree_solve_diag_bwd_dbl", "spldlt_tree_solve_fwd_posdef_dbl",
     "spldlt_tree_solve_bwd_posdef_dbl", "sylver_b200_device_count", "sylver_b200_version",
-    "sylver_b200_akeep_view", "sylver_b200_symbolic_tree_cmap", "sylver_b200_numeric_tree_timings",
+    "sylver_b200_akeep_view", "sylver_b200_symbolic_tree_cmap", "sylver_b200_numeric_tree_timings", "sylver_b200_numeric_tree_split_info",
     "sylver_b200_fkeep_tree", "sylver_b200_factor_front_posdef", "sylver_b200_factor_front_indef",
     "sylver_b200_bench_dmma", "sylver_b200_bench_copy", "sylver_b200_akeep_tree",
     "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_fkeep_tree.restype = vp
     L.sylver_b200_fkeep_tree.argtypes = [vp]
     L.sylver_b200_numeric_tree_timings.argtypes = [vp, dp]
+    L.sylver_b200_numeric_tree_split_info.argtypes = [vp, vp]
     L.sylver_b200_numeric_tree_get_front.argtypes = [vp, C.c_int, ip, ip, vp, vp]
     L.sylver_b200_factor_front_posdef.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                                   C.POINTER(C.c_float)]
@@ -364,6 +365,14 @@ class Solver:
         if not tree or self.L.sylver_b200_numeric_tree_timings(tree, out) != 0:
             return None
         return dict(device_s=out[0], h2d_s=out[1], wall_s=out[2], launches=int(out[3]))
+
+    def split_info(self):
+        """(split fronts in the tree, split fronts this rank works on, pieces sent) of the last factorization."""
+        out = (C.c_int * 3)()
+        tree = self.L.sylver_b200_fkeep_tree(self.fkeep)
+        if not tree or self.L.sylver_b200_numeric_tree_split_info(tree, out) != 0:
+            return None
+        return int(out[0]), int(out[1]), int(out[2])
 
     def solve(self, b, job: int = 0):
         x = np.array(b, dtype=np.float64, order="F", copy=True)

@@ -368,6 +368,12 @@ int sylver_b200_numeric_tree_timings(void const* tree, double* out4) {
    return 0;
 }
 
+int sylver_b200_numeric_tree_split_info(void const* tree, int* out3) {
+   if (!tree) return -1;
+   numeric_tree_split_info(static_cast<const NumericTree*>(tree), out3);
+   return 0;
+}
+
 int sylver_b200_numeric_tree_profile(void const* tree, double* out, int cap) {
    if (!tree) return -1;
    return numeric_tree_profile(static_cast<const NumericTree*>(tree), out, cap);

@@ -229,7 +229,6 @@ void plan_contrib_arena(NumericTree* nt) {
    const int N = st->nnodes;
    const int me = nt->rank;
    if ((int)nt->owner.size() != N) nt->owner.assign(N, 0);
-   const std::vector<int>& own = nt->owner;
    nt->ldc.resize(N);
    nt->coff.assign(N, 0);
    for (int f = 0; f < N; ++f) nt->ldc[f] = round_up(std::max(st->nrow[f] - st->ncol[f], 1), 4);
@@ -240,12 +239,12 @@ void plan_contrib_arena(NumericTree* nt) {
          const int f = st->level_nodes[i];
          const long k = st->nrow[f] - st->ncol[f];
          const int p = st->parent[f];
-         const bool held = own[f] == me || (p < N && own[p] == me);
+         const bool held = in_dest(nt, f, me) || (p < N && in_dest(nt, p, me));
          if (k > 0 && held) nt->coff[f] = sa.alloc((long)nt->ldc[f] * k);
       }
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
-         if (own[f] != me) continue;
+         if (!in_dest(nt, f, me)) continue;
          // children were consumed by this front's assembly
          for (int ci = st->child_ptr[f]; ci < st->child_ptr[f + 1]; ++ci) {
             const int c = st->child_list[ci];
@@ -255,7 +254,7 @@ void plan_contrib_arena(NumericTree* nt) {
          // a block sent to a remote parent is free once the level's exchange is issued
          const int p = st->parent[f];
          const long k = st->nrow[f] - st->ncol[f];
-         if (k > 0 && p < N && own[p] != me) sa.release(nt->coff[f], (long)nt->ldc[f] * k);
+         if (k > 0 && p < N && !in_dest(nt, p, me)) sa.release(nt->coff[f], (long)nt->ldc[f] * k);
       }
    }
    nt->C_doubles = sa.peak + 4;
@@ -290,26 +289,140 @@ void plan_owned_levels(NumericTree* nt) {
    nt->d_lvl_nodes = dev_upload(nt->lvl_nodes);
 }
 
+// Split fronts, the batched lists without them, and the pieces of contribution blocks that
+// cross GPUs.  A block of an unsplit front is one piece held by its owner; the block of a
+// split front is held tile column by tile column (the DMMA tile grid of k_gemm_batched mode 1)
+// by the members of its group.  Every rank that works on the parent needs every piece.  All
+// ranks enumerate (level, front, piece, destination) in the same order, so the sends and
+// receives of a rank pair match up.
+static void plan_split(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes, me = nt->rank, nb = nt->nb;
+   nt->fac_ptr.assign(st->nlevels + 1, 0);
+   nt->fac_nodes.clear();
+   nt->splits.assign(st->nlevels, {});
+   nt->csends.assign(st->nlevels, {});
+   nt->crecvs.assign(st->nlevels, {});
+   std::vector<int> split_fronts;
+   size_t stage = 0;
+   for (int l = 0; l < st->nlevels; ++l) {
+      for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
+         const int f = st->level_nodes[i];
+         if (nt->splitP[f] > 1) {
+            if (in_dest(nt, f, me)) {
+               SplitPlan sp;
+               sp.f = f; sp.P = nt->splitP[f]; sp.q = nt->splitQ[f]; sp.g0 = nt->grp0[f];
+               sp.slot = (int)split_fronts.size();
+               split_fronts.push_back(f);
+               stage = std::max(stage, (size_t)nt->m[f] * nb);
+               nt->splits[l].push_back(sp);
+            }
+         } else if (nt->owner[f] == me) {
+            nt->fac_nodes.push_back(f);
+         }
+         // ---- pieces of f's contribution block and who needs them ----
+         const int p = st->parent[f];
+         const int k = st->nrow[f] - st->ncol[f];
+         if (p >= N || k == 0 || nt->world <= 1) continue;
+         const int d0 = nt->splitP[p] > 1 ? nt->grp0[p] : nt->owner[p];
+         const int d1 = d0 + (nt->splitP[p] > 1 ? nt->splitP[p] : 1);
+         auto emit = [&](int src, long off, size_t count) {
+            for (int d = d0; d < d1; ++d) {
+               if (d == src) continue;
+               if (src == me) nt->csends[l].push_back(Piece{f, d, off, count});
+               else if (d == me) nt->crecvs[l].push_back(Piece{f, src, off, count});
+            }
+         };
+         const long ldc = nt->ldc[f];
+         if (nt->splitP[f] > 1) {
+            const int odd = st->ncol[f] & 1;      // the tile grid starts at the even column n & ~1
+            const int TR = (k + odd + GT_BN - 1) / GT_BN;
+            for (int tj = 0; tj < TR; ++tj) {
+               const int c0 = std::max(0, tj * GT_BN - odd), c1 = std::min(k, (tj + 1) * GT_BN - odd);
+               if (c1 <= c0) continue;
+               emit(nt->grp0[f] + tj % nt->splitP[f], c0 * ldc + c0, (size_t)((c1 - c0) * ldc - c0));
+            }
+         } else {
+            emit(nt->owner[f], 0, (size_t)(k * ldc));
+         }
+      }
+      nt->fac_ptr[l + 1] = (int)nt->fac_nodes.size();
+   }
+   // sub-communicators: every rank of the world walks the same (deterministic) list of groups
+   if (nt->world > 1) {
+      std::vector<std::pair<int, int>> groups;
+      for (int f = 0; f < N; ++f)
+         if (nt->splitP[f] > 1) {
+            const std::pair<int, int> g(nt->grp0[f], nt->splitP[f]);
+            if (std::find(groups.begin(), groups.end(), g) == groups.end()) groups.push_back(g);
+         }
+      for (auto& g : groups) {
+         const int gid = comm_subgroup(g.first, g.second);
+         if (gid == -2) throw CudaFailure{-52};
+         for (auto& lv : nt->splits)
+            for (SplitPlan& sp : lv)
+               if (sp.g0 == g.first && sp.P == g.second) sp.gid = gid;
+      }
+   }
+   if (nt->d_fac_nodes) cudaFree(nt->d_fac_nodes);
+   nt->d_fac_nodes = dev_upload(nt->fac_nodes);
+   if (!split_fronts.empty()) {
+      nt->d_split_fronts = dev_upload(split_fronts);
+      nt->d_splitP = dev_upload(nt->splitP);
+      nt->d_splitQ = dev_upload(nt->splitQ);
+      nt->stage_doubles = stage;
+      CU_TRY(cudaMalloc(&nt->d_stage, stage * sizeof(double)));
+      CU_TRY(cudaMalloc(&nt->d_Wsplit, (size_t)nb * nb * sizeof(double)));
+   }
+   if (!nt->d_zero) {
+      CU_TRY(cudaMalloc(&nt->d_zero, 4 * sizeof(int)));
+      CU_TRY(cudaMemset(nt->d_zero, 0, 4 * sizeof(int)));
+   }
+   if (nt->world > 1) {
+      std::vector<int> so(N);
+      for (int f = 0; f < N; ++f) so[f] = in_dest(nt, f, me) ? me : (me + 1) % nt->world;
+      nt->d_scat_owner = dev_upload(so);
+   }
+}
+
 static void build_posdef_plan(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
    const int nb = nt->nb;
    nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N);
    nt->loff.resize(N);
-   partition_tree(*st, nt->world, nt->owner);
    const int me = nt->rank;
+   {
+      // fronts above the partition cut whose rank group has several members are split over the
+      // group when they are wide enough for the panel broadcasts to pay (SYLVER_B200_SPLIT=0
+      // keeps every front on one GPU; SYLVER_B200_SPLIT_MIN = minimum fully-summed columns)
+      std::vector<int> grpn;
+      partition_tree(*st, nt->world, nt->owner, &nt->grp0, &grpn);
+      nt->splitP.assign(N, 1);
+      nt->splitQ.assign(N, 0);
+      const char* se = getenv("SYLVER_B200_SPLIT");
+      const char* sm = getenv("SYLVER_B200_SPLIT_MIN");
+      const int split_min = sm ? atoi(sm) : 1024;
+      if (nt->world > 1 && !(se && se[0] == '0'))
+         for (int f = 0; f < N; ++f)
+            if (grpn[f] >= 2 && st->ncol[f] >= split_min) {
+               nt->splitP[f] = grpn[f];
+               nt->splitQ[f] = me - nt->grp0[f];
+            }
+   }
    long loff = 0;
    for (int f = 0; f < N; ++f) {
       nt->m[f] = st->nrow[f];
       nt->n[f] = st->ncol[f];
       nt->ldl[f] = round_up(nt->m[f], 4);
       nt->loff[f] = loff;
-      if (nt->owner[f] == me) loff += (long)nt->ldl[f] * nt->n[f];
+      if (in_dest(nt, f, me)) loff += (long)nt->ldl[f] * nt->n[f];
    }
    nt->L_doubles = loff + 4;
    plan_contrib_arena(nt);
    plan_exchanges(*st, nt->owner, me, nt->sends, nt->recvs);
    plan_owned_levels(nt);
+   plan_split(nt);
 
    // work lists
    std::vector<int> prefix;
@@ -318,9 +431,9 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->levels.resize(st->nlevels);
    for (int l = 0; l < st->nlevels; ++l) {
       LevelPlan& lp = nt->levels[l];
-      lp.first = nt->lvl_ptr[l];
-      lp.count = nt->lvl_ptr[l + 1] - lp.first;
-      const int* fr = nt->lvl_nodes.data() + lp.first;
+      lp.first = nt->fac_ptr[l];
+      lp.count = nt->fac_ptr[l + 1] - lp.first;
+      const int* fr = nt->fac_nodes.data() + lp.first;
       lp.max_children = 0;
       int maxn = 0;
       for (int i = 0; i < lp.count; ++i) {
@@ -339,6 +452,18 @@ static void build_posdef_plan(NumericTree* nt) {
             for (int j0 = 0; j0 < k; j0 += 32) asmw.push_back(make_int2(c, j0));
          }
          lp.asm_work.emplace_back(off, (int)(asmw.size() - off));
+      }
+      // split fronts of this level: every member walks all children (it holds all their blocks)
+      // and adds the columns it owns
+      for (SplitPlan& sp : nt->splits[l]) {
+         const int f = sp.f;
+         for (int q = 0; q < st->nchild[f]; ++q) {
+            const size_t off = asmw.size();
+            const int c = st->child_list[st->child_ptr[f] + q];
+            const int k = nt->m[c] - nt->n[c];
+            for (int j0 = 0; j0 < k; j0 += 32) asmw.push_back(make_int2(c, j0));
+            sp.asm_work.emplace_back(off, (int)(asmw.size() - off));
+         }
       }
       // block-column steps
       const int nsteps = (maxn + nb - 1) / nb;
@@ -421,18 +546,19 @@ static void build_posdef_plan(NumericTree* nt) {
    // algorithmic flops per kernel class (lower triangle only, multiply and add counted)
    for (int c = 0; c < KC_COUNT; ++c) nt->prof_flops[c] = 0;
    for (int f = 0; f < N; ++f) {
-      if (nt->owner[f] != me) continue;
+      if (!in_dest(nt, f, me)) continue;
+      const double share = 1.0 / nt->splitP[f];      // split fronts: this member's part
       const double m = nt->m[f], n = nt->n[f];
       for (int p0 = 0; p0 < nt->n[f]; p0 += nb) {
          const double pw = std::min(nb, nt->n[f] - p0), p1 = p0 + pw;
-         nt->prof_flops[KC_POTRF] += pw * pw * pw / 3.0;
-         nt->prof_flops[KC_TRSM] += (m - p1) * pw * pw;
+         nt->prof_flops[KC_POTRF] += share * pw * pw * pw / 3.0;
+         nt->prof_flops[KC_TRSM] += share * (m - p1) * pw * pw;
          // sum_{c=p1}^{n-1} (m - c) lower-triangle entries, 2*pw flops each
          const double cnt = (n - p1) * m - (n * (n - 1) - p1 * (p1 - 1)) / 2.0;
-         nt->prof_flops[KC_UPDATE] += 2.0 * pw * cnt;
+         nt->prof_flops[KC_UPDATE] += share * 2.0 * pw * cnt;
       }
       const double k = m - n;
-      nt->prof_flops[KC_CONTRIB] += n * k * (k + 1);
+      nt->prof_flops[KC_CONTRIB] += share * n * k * (k + 1);
    }
    nt->W_doubles = wmax;
    nt->d_prefix = dev_upload(prefix);
@@ -450,6 +576,7 @@ void upload_geometry(NumericTree* nt) {
    T.parent = st->d_parent; T.nchild = st->d_nchild; T.cmap = st->d_cmap;
    T.L = nt->d_L; T.C = nt->d_C;
    T.fchild = st->d_fchild; T.pinvoff = st->d_pinvoff; T.pinv = st->d_pinv;
+   T.splitP = nt->d_splitP; T.splitQ = nt->d_splitQ;
 }
 
 // Contribution blocks (factorization) or solve work vectors whose parent front lives on another
@@ -473,6 +600,121 @@ static void issue_exchange(NumericTree* nt, int l, double* base, const std::vect
    if (rc) throw CudaFailure{-52};
 }
 
+// Contribution pieces whose destination ranks differ from their holder (see plan_split).
+static void issue_contrib_exchange(NumericTree* nt, int l) {
+   if (nt->world <= 1) return;
+   const auto& sd = nt->csends[l];
+   const auto& rv = nt->crecvs[l];
+   if (sd.empty() && rv.empty()) return;
+   int rc = comm_group_start();
+   for (const Piece& x : sd) rc |= comm_send(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream);
+   for (const Piece& x : rv) rc |= comm_recv(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream);
+   rc |= comm_group_end();
+   if (rc) throw CudaFailure{-52};
+}
+
+// One front split over a rank group (top of the tree).  Block column j of the
+// fully-summed part belongs to member j % P, tile column j of the contribution block to
+// member j % P.  The owner factorizes its block column (potrf + panel solve) and broadcasts
+// the panel (rows p0..m) to the group; every member then applies it to the block columns it
+// owns.  Depth-1 look-ahead: the owner of the next block column updates that column first and
+// runs its factorization + broadcast on the second stream beside the rest of the update.
+static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launches) {
+   cudaStream_t s = nt->stream;
+   cudaStream_t s2 = nt->stream2 ? nt->stream2 : nt->stream;
+   const DevTree& T = nt->T;
+   const int nb = nt->nb, f = sp.f, m = nt->m[f], n = nt->n[f], ldl = nt->ldl[f];
+   const int P = sp.P, q = sp.q, me = nt->rank;
+   const int NB = (n + nb - 1) / nb;
+   const int* d_fr = nt->d_split_fronts + sp.slot;
+   const TileBatch b{d_fr, nt->d_zero, 1};
+   double* Lf = nt->d_L + nt->loff[f];
+   auto assemble = [&](int part) {
+      for (auto& w : sp.asm_work) {
+         if (w.second == 0) continue;
+         ProfScope ps(nt, KC_ASSEMBLE);
+         k_assemble<<<w.second, 256, 0, s>>>(T, nt->d_asm_work + w.first, part);
+         ++launches;
+      }
+   };
+   auto panel = [&](int si) {
+      const int p0 = si * nb, pw = std::min(nb, n - p0), rows = m - p0;
+      const int own = sp.g0 + si % P;
+      const int wld = round_up(pw, 4);
+      if (me == own) {
+         {
+            ProfScope ps(nt, KC_POTRF, s2);
+            k_potrf_inv_reg<<<1, PR_THREADS, 0, s2>>>(T, d_fr, si, nb, nt->d_Wsplit, wld, nt->d_fail);
+            ++launches;
+         }
+         if (m > p0 + pw) {
+            const int tiles = (m - ((p0 + pw) & ~1) + GT_BM - 1) / GT_BM;
+            ProfScope ps(nt, KC_TRSM, s2);
+            k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s2>>>(T, b, 2, si, nb, nt->d_Wsplit, wld, 0, 1);
+            ++launches;
+         }
+         CU_TRY(cudaMemcpy2DAsync(nt->d_stage, (size_t)rows * sizeof(double), Lf + (size_t)p0 * ldl + p0,
+                                  (size_t)ldl * sizeof(double), (size_t)rows * sizeof(double), pw,
+                                  cudaMemcpyDeviceToDevice, s2));
+      }
+      if (comm_bcast(nt->d_stage, (size_t)rows * pw, own, sp.gid, s2)) throw CudaFailure{-52};
+      if (me != own)
+         CU_TRY(cudaMemcpy2DAsync(Lf + (size_t)p0 * ldl + p0, (size_t)ldl * sizeof(double), nt->d_stage,
+                                  (size_t)rows * sizeof(double), (size_t)rows * sizeof(double), pw,
+                                  cudaMemcpyDeviceToDevice, s2));
+   };
+   // trailing update by block column si: tile columns tstart, tstart + tstep, ... of the grid that
+   // starts at column (si + 1) * nb (tile column tj = block column si + 1 + tj)
+   auto update = [&](int si, int tstart, int tstep, bool first_only) {
+      const int base = (si + 1) * nb;
+      if (n <= base) return;
+      const int TR = (m - base + GT_BM - 1) / GT_BM, TC = (n - base + GT_BN - 1) / GT_BN;
+      int tiles = 0;
+      if (first_only) tiles = TR;
+      else
+         for (int tj = tstart; tj < TC; tj += tstep) tiles += TR - tj;
+      if (tiles == 0) return;
+      ProfScope ps(nt, KC_UPDATE);
+      k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, si, nb, nullptr, 0, tstart, tstep);
+      ++launches;
+   };
+   assemble(0);
+   if (s2 != s) {
+      CU_TRY(cudaEventRecord(nt->ev_next, s));
+      CU_TRY(cudaStreamWaitEvent(s2, nt->ev_next, 0));
+   }
+   panel(0);
+   if (s2 != s) CU_TRY(cudaEventRecord(nt->ev_panel, s2));
+   for (int si = 0; si < NB; ++si) {
+      if (s2 != s) CU_TRY(cudaStreamWaitEvent(s, nt->ev_panel, 0));      // panel si is here
+      if (si + 1 >= NB) break;
+      if (q == (si + 1) % P) {
+         update(si, 0, 1, true);
+         if (s2 != s) {
+            CU_TRY(cudaEventRecord(nt->ev_next, s));
+            CU_TRY(cudaStreamWaitEvent(s2, nt->ev_next, 0));
+         }
+      }
+      panel(si + 1);
+      if (s2 != s) CU_TRY(cudaEventRecord(nt->ev_panel, s2));
+      int t0 = ((q - (si + 1)) % P + P) % P;
+      if (t0 == 0) t0 = P;
+      update(si, t0, P, false);
+   }
+   if (m > n) {
+      const int base = n & ~1;
+      const int TR = (m - base + GT_BM - 1) / GT_BM;
+      int tiles = 0;
+      for (int tj = q; tj < TR; tj += P) tiles += TR - tj;
+      if (tiles > 0) {
+         ProfScope ps(nt, KC_CONTRIB);
+         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, q, P);
+         ++launches;
+      }
+   }
+   assemble(1);
+}
+
 static void issue_posdef(NumericTree* nt) {
    SymbolicTree* st = nt->st;
    cudaStream_t s = nt->stream;
@@ -487,14 +729,15 @@ static void issue_posdef(NumericTree* nt) {
       ProfScope ps(nt, KC_SCATTER);
       k_scatter_a<<<blocks, 256, 0, s>>>(T, st->nent, st->d_nlist, st->d_anode, st->d_nrow, st->d_ncol,
                                          nt->d_aval, nt->d_scaling, st->d_rlist, st->d_rptr,
-                                         nt->world > 1 ? nt->d_owner : nullptr, nt->rank);
+                                         nt->world > 1 ? nt->d_scat_owner : nullptr, nt->rank);
       ++launches;
    }
    for (size_t l = 0; l < nt->levels.size(); ++l) {
       const LevelPlan& lp = nt->levels[l];
-      const int* d_fr = nt->d_lvl_nodes + lp.first;
+      const int* d_fr = nt->d_fac_nodes + lp.first;
       if (lp.count == 0) {
-         issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
+         for (const SplitPlan& sp : nt->splits[l]) issue_split_front(nt, sp, launches);
+         issue_contrib_exchange(nt, (int)l);
          continue;
       }
       auto assemble = [&](int part) {
@@ -513,8 +756,10 @@ static void issue_posdef(NumericTree* nt) {
             k_potrf_inv<32><<<ls.cnt, 128, PotrfCfg<32>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
          else if (ls.wld <= 64)
             k_potrf_inv<64><<<ls.cnt, 256, PotrfCfg<64>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
-         else
+         else if (nt->potrf_old)
             k_potrf_inv<128><<<ls.cnt, 512, PotrfCfg<128>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         else
+            k_potrf_inv_reg<<<ls.cnt, PR_THREADS, 0, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
          ++launches;
       };
       auto trsm = [&](size_t si, cudaStream_t q) {
@@ -522,7 +767,7 @@ static void issue_posdef(NumericTree* nt) {
          if (ls.trsm_tiles == 0) return;
          TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
          ProfScope ps(nt, KC_TRSM, q);
-         k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld);
+         k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld, 0, 1);
          ++launches;
       };
       auto update = [&](size_t si, int sub, cudaStream_t q) {
@@ -532,7 +777,7 @@ static void issue_posdef(NumericTree* nt) {
          const size_t off = sub == 0 ? ls.upd_prefix : (sub == 1 ? ls.updn_prefix : ls.updr_prefix);
          TileBatch b{d_fr, nt->d_prefix + off, ls.cnt};
          ProfScope ps(nt, KC_UPDATE, q);
-         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, (int)si, nb, nullptr, sub);
+         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, (int)si, nb, nullptr, 0, sub == 2 ? 1 : 0, 1);
          ++launches;
       };
       // Look-ahead (few, large fronts): as soon as the next block column has received its
@@ -567,11 +812,12 @@ static void issue_posdef(NumericTree* nt) {
       if (lp.contrib_tiles > 0) {
          TileBatch b{d_fr, nt->d_prefix + lp.contrib_prefix, lp.count};
          ProfScope ps(nt, KC_CONTRIB);
-         k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0);
+         k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, 0, 1);
          ++launches;
       }
       assemble(1);      // children -> contribution block (after this front's own Schur complement)
-      issue_exchange(nt, (int)l, nt->d_C, nt->coff, nullptr);
+      for (const SplitPlan& sp : nt->splits[l]) issue_split_front(nt, sp, launches);
+      issue_contrib_exchange(nt, (int)l);
    }
    if (nt->world > 1 && comm_allreduce_max_int(nt->d_fail, 1, s)) throw CudaFailure{-52};
    CU_TRY(cudaGetLastError());
@@ -671,6 +917,10 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       CU_TRY(cudaEventCreate(&nt->ev0));
       CU_TRY(cudaEventCreate(&nt->ev1));
       {
+         const char* po = getenv("SYLVER_B200_POTRF_OLD");
+         nt->potrf_old = po && po[0] == '1';
+      }
+      {
          const char* la = getenv("SYLVER_B200_LOOKAHEAD");
          if (!(la && la[0] == '0')) {
             CU_TRY(cudaStreamCreateWithFlags(&nt->stream2, cudaStreamNonBlocking));
@@ -745,6 +995,8 @@ void numeric_tree_destroy(NumericTree* nt) {
    cudaFree(nt->d_W); cudaFree(nt->d_aval); cudaFree(nt->d_scaling); cudaFree(nt->d_fail);
    cudaFree(nt->d_prefix); cudaFree(nt->d_asm_work); cudaFree(nt->d_xw); cudaFree(nt->d_xwoff);
    cudaFree(nt->d_child_ptr); cudaFree(nt->d_child_list);
+   cudaFree(nt->d_splitP); cudaFree(nt->d_splitQ); cudaFree(nt->d_scat_owner); cudaFree(nt->d_fac_nodes);
+   cudaFree(nt->d_split_fronts); cudaFree(nt->d_zero); cudaFree(nt->d_stage); cudaFree(nt->d_Wsplit);
    cudaFree(nt->d_lvl_nodes); cudaFree(nt->d_owner); cudaFree(nt->d_all_nodes); cudaFree(nt->d_xbuf); cudaFree(nt->d_xpack_off);
    if (nt->ev0) cudaEventDestroy(nt->ev0);
    if (nt->ev1) cudaEventDestroy(nt->ev1);
@@ -761,6 +1013,16 @@ void numeric_tree_timings(const NumericTree* nt, double* out4) {
    out4[1] = nt->t_h2d;
    out4[2] = nt->t_wall;
    out4[3] = (double)nt->launches;
+}
+
+void numeric_tree_split_info(const NumericTree* nt, int* out3) {
+   out3[0] = out3[1] = out3[2] = 0;
+   for (size_t f = 0; f < nt->splitP.size(); ++f)
+      if (nt->splitP[f] > 1) {
+         ++out3[0];
+         if (in_dest(nt, (int)f, nt->rank)) ++out3[1];
+      }
+   for (auto& l : nt->csends) out3[2] += (int)l.size();
 }
 
 long numeric_tree_bytes(const NumericTree* nt, long* factor_bytes, long* contrib_bytes) {

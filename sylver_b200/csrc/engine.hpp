@@ -70,7 +70,8 @@ struct Xfer {
 };
 // Deterministic mapping of fronts to ranks and the resulting per-level exchange lists
 // (host only; identical on every rank).
-void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner);
+void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner, std::vector<int>* grp0 = nullptr,
+                    std::vector<int>* grpn = nullptr);
 void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int rank,
                     std::vector<std::vector<Xfer>>& sends, std::vector<std::vector<Xfer>>& recvs);
 
@@ -83,6 +84,9 @@ void numeric_tree_destroy(NumericTree* nt);
 // job: 1 fwd, 2 diag, 3 bwd, 4 diag+bwd, 0 all.  x host or device, already permuted.
 int numeric_tree_solve(const NumericTree* nt, int job, int nrhs, double* x, int ldx);
 void numeric_tree_timings(const NumericTree* nt, double* out4);
+// out3: fronts split over a rank group in the whole tree, those this rank is a member of, and
+// contribution pieces this rank sends per factorization
+void numeric_tree_split_info(const NumericTree* nt, int* out3);
 bool numeric_tree_posdef(const NumericTree* nt);
 // Debug / test access: copy one front's L panel (m x n, ld m) and contribution
 // ((m-n)^2, ld m-n) to host buffers (either may be null). Returns 0 or <0.

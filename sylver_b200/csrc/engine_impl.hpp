@@ -119,6 +119,19 @@ struct LevelPlan {
    size_t contrib_prefix;
 };
 
+// One contiguous piece of a contribution block crossing GPUs (offset relative to coff[f]).
+struct Piece {
+   int f, peer;
+   long off;
+   size_t count;
+};
+// A front whose block columns are dealt round-robin to the ranks [g0, g0 + P) (top of the
+// tree): this rank is member q; panels travel by broadcast on sub-communicator gid.
+struct SplitPlan {
+   int f = -1, P = 1, q = 0, g0 = 0, gid = -1, slot = 0;
+   std::vector<std::pair<size_t, int>> asm_work;
+};
+
 enum KClass { KC_SCATTER = 0, KC_ZERO, KC_ASSEMBLE, KC_POTRF, KC_TRSM, KC_UPDATE, KC_CONTRIB, KC_COUNT };
 
 
@@ -150,6 +163,7 @@ struct NumericTree {
    cudaGraphExec_t graph = nullptr;
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
    bool profile = false;
+   bool potrf_old = false;               // SYLVER_B200_POTRF_OLD=1: shared-memory k_potrf_inv<128> (A/B runs)
    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
    double prof_ms[KC_COUNT] = {0};
    long prof_launches[KC_COUNT] = {0};
@@ -172,6 +186,18 @@ struct NumericTree {
    int* d_all_nodes = nullptr;           // st->level_nodes (all fronts), for the solve broadcasts
    int* d_xpack_off = nullptr;
    double* d_xbuf = nullptr; size_t xbuf_cap = 0;
+   // ---- fronts split over a rank group (posdef): block-column cyclic, panel broadcasts ----
+   std::vector<int> grp0, splitP, splitQ;         // per front; splitP == 1: not split
+   int *d_splitP = nullptr, *d_splitQ = nullptr;
+   int* d_scat_owner = nullptr;                   // == rank for every front this rank holds a copy of
+   std::vector<int> fac_ptr, fac_nodes;           // owned, unsplit fronts per level (the batched path)
+   int* d_fac_nodes = nullptr;
+   std::vector<std::vector<SplitPlan>> splits;    // per level: split fronts this rank is a member of
+   std::vector<std::vector<Piece>> csends, crecvs;   // per level: contribution pieces crossing GPUs
+   int* d_split_fronts = nullptr;
+   int* d_zero = nullptr;
+   double* d_stage = nullptr; size_t stage_doubles = 0;
+   double* d_Wsplit = nullptr;
    // ---- indefinite (APTP) path: dynamic geometry, see engine_indef.cu ----
    struct Chunk { double* ptr; size_t cap, used; };
    std::vector<Chunk> chunks;            // factor arena: L panel + D^-1 + perm per front, bump allocated
@@ -212,8 +238,12 @@ struct ProfScope {
 }  // namespace
 
 
-// partition.cpp
-void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner);
+
+// does rank r hold (and work on) front f?  split fronts: every member of the group
+static inline bool in_dest(const NumericTree* nt, int f, int r) {
+   if (!nt->splitP.empty() && nt->splitP[f] > 1) return r >= nt->grp0[f] && r < nt->grp0[f] + nt->splitP[f];
+   return nt->owner[f] == r;
+}
 
 // engine_indef.cu
 void run_indef(NumericTree* nt, sylver_inform_c* stats);

@@ -423,7 +423,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
             }
             {
                ProfScope ps(nt, KC_UPDATE);
-               k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0);
+               k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
                ++launches;
             }
          }
@@ -436,7 +436,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          if (con_prefix[cnt] > 0) {
             TileBatch cb{d_fr, d_con, cnt};
             ProfScope ps(nt, KC_CONTRIB);
-            k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0);
+            k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0, 0, 1);
             ++launches;
          }
          assemble(1);

@@ -59,7 +59,21 @@ struct DevTree {
    const int* fchild;    // [2*nnodes], -1 = unused slot; nullptr disables the fusion
    const long* pinvoff;  // [2*nnodes]
    const int* pinv;
+   // ---- fronts split over a rank group (multi-GPU, top of the tree) ----
+   // splitP[f] > 1: the block columns (width 128) of front f are dealt round-robin to the
+   // splitP[f] members of its group and this rank is member splitQ[f]; the extend-add only
+   // touches the columns this rank owns.  nullptr: no front is split.
+   const int* splitP;
+   const int* splitQ;
 };
+
+// Does member q of a P-way split own column `col` of a front with n fully-summed columns?
+// L panel: block column col/128.  Contribution block: tile column of the DMMA tile grid, which
+// starts at the even column n & ~1 (k_gemm_batched mode 1).
+__device__ __forceinline__ bool split_owns(int P, int q, int n, int col) {
+   const int blk = (col < n) ? (col >> 7) : ((col - (n & ~1)) >> 7);
+   return blk % P == q;
+}
 
 // ---------------------------------------------------------------------------
 // PTX helpers: FP64 tensor-core MMA, mbarrier, TMA bulk copy
@@ -149,6 +163,13 @@ struct GemmTile {
    bool prefetch;
    int pf_c0, pf_c1;  // tile-relative column range worth prefetching
    int pf_lines;      // 128 B lines per column
+   // fused extend-add (contribution tiles): the children's entries the epilogue gathers are
+   // pulled into L2 by the producer warp while the tensor cores work
+   const double* gsrc[2];
+   const int* gmap[2];    // parent contribution row -> child row (-1: none), increasing
+   int gld[2];
+   int g_r0, g_c0;        // contribution-relative row / column of the tile origin
+   int g_k;               // order of the parent's contribution block
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMERS * 32) : "memory"); }
@@ -199,6 +220,37 @@ __device__ __forceinline__ bool gemm_tile_mainloop(const GemmTile& t, double* sm
                tma_bulk_g2s(As + kc * GT_LDS, t.A + (size_t)(k0 + kc) * t.lda, abytes, &full[s]);
             else if (!same)
                tma_bulk_g2s(Bs + kc * GT_LDS, t.B + (size_t)(k0 + kc) * t.ldb, bbytes, &full[s]);
+         }
+         if (kb == min(nk, GT_STAGES) - 1 && (t.gsrc[0] || t.gsrc[1])) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+               if (!t.gsrc[s2]) continue;
+               // child rows hit by this tile's rows: [rlo, rhi]
+               int rlo = 0x7fffffff, rhi = -1;
+#pragma unroll
+               for (int q = 0; q < 4; ++q) {
+                  const int r = t.g_r0 + lane + 32 * q;
+                  const int v = (r >= 0 && r < t.g_k) ? t.gmap[s2][r] : -1;
+                  if (v >= 0) { rlo = min(rlo, v); rhi = max(rhi, v); }
+               }
+#pragma unroll
+               for (int o = 16; o > 0; o >>= 1) {
+                  rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+                  rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+               }
+               if (rhi < 0) continue;
+               for (int cc = lane; cc < GT_BN; cc += 32) {
+                  const int c = t.g_c0 + cc;
+                  const int ic = (c >= 0 && c < t.g_k) ? t.gmap[s2][c] : -1;
+                  if (ic < 0) continue;
+                  const int lo = max(rlo, ic);
+                  if (lo > rhi) continue;
+                  const char* p0 = reinterpret_cast<const char*>(t.gsrc[s2] + (size_t)ic * t.gld[s2] + lo);
+                  const char* p1 = reinterpret_cast<const char*>(t.gsrc[s2] + (size_t)ic * t.gld[s2] + rhi);
+                  for (const char* p = p0; p <= p1; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+               }
+            }
          }
          if (kb == min(nk, GT_STAGES) - 1 && t.prefetch) {
             // pull the destination tile into L2 while the tensor cores work
@@ -282,11 +334,13 @@ __device__ __forceinline__ int find_front(const TileBatch& b, int item) {
 // mode 1: contribution block:  C[r-n][c-n] = beta*C - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
 // mode 2: panel solve with the inverted diagonal block W (pw x pw, ld wld):
 //         L[r][p0+c] = sum_k L[r][p0+k] W[c][k],  r in [p0+pw, m)
-// nb is the block-column width; `step` the block column index.  For mode 0, `wld` selects a
-// subset of the trailing tiles (look-ahead scheduling): 0 all, 1 only the first tile column
-// (the next block column), 2 everything but the first tile column.
+// nb is the block-column width; `step` the block column index.  Modes 0 and 1 enumerate the
+// tile columns tstart, tstart + tstep, ... of the tile grid (look-ahead scheduling: the grid
+// size limits a launch to the first tile column, tstart = 1 skips it; split fronts: the tile
+// columns this rank owns).
 static __global__ void __launch_bounds__(GT_THREADS, 1)
-k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld) {
+k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld,
+               int tstart, int tstep) {
    extern __shared__ __align__(128) double smem[];
    const int item = blockIdx.x;
    const int fi = find_front(batch, item);
@@ -357,9 +411,9 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       const int cend = (mode == 0) ? n : m;
       const int TR = (m - base + GT_BM - 1) / GT_BM;
       const int TC = (cend - base + GT_BN - 1) / GT_BN;
-      if (mode == 0 && wld == 2) local += TR;       // skip the first tile column
-      int tj = 0;
-      while (tj < TC && local >= TR - tj) { local -= TR - tj; ++tj; }
+      int tj = tstart;
+      while (tj < TC && local >= TR - tj) { local -= TR - tj; tj += tstep; }
+      if (tj >= TC) return;
       const int ti = tj + local;
       i0 = base + ti * GT_BM;
       j0 = base + tj * GT_BN;
@@ -385,6 +439,18 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    t.pf_c0 = max(0, clo - j0);
    t.pf_c1 = min(GT_BN, chi - j0);
    t.pf_lines = (min(GT_BM, m - i0) * 8 + 127) / 128;
+   t.gsrc[0] = t.gsrc[1] = nullptr;
+   if (op == 1 && T.fchild) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+         const int fc = T.fchild[2 * f + s];
+         if (fc < 0) continue;
+         t.gsrc[s] = T.C + T.coff[fc];
+         t.gld[s] = T.ldc[fc];
+         t.gmap[s] = T.pinv + T.pinvoff[2 * f + s];
+      }
+      t.g_r0 = i0 - n; t.g_c0 = j0 - n; t.g_k = m - n;
+   }
    if (!gemm_tile_mainloop(t, smem)) return;
 
    // ---- coalesced epilogue: warp w owns tile columns w*8 .. w*8+7, lanes stride the rows ----
@@ -395,26 +461,27 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    // reference adds afterwards (assemble_contrib_block, src/kernels/assemble.hxx:343-517)
    // are gathered here through the parent-row -> child-row maps, so the block is written
    // once instead of written, re-read and re-written (8 + 8 B per entry instead of 8 + 24).
-   const double* fsrc[2] = {nullptr, nullptr};
-   const int* fmap[2] = {nullptr, nullptr};
-   int fld[2] = {0, 0};
-   int fir[2][4];
-   if (op == 1 && T.fchild) {
+   // All map entries a warp needs (4 row groups, its 8 columns) are loaded up front in one
+   // batch, and the gathers are predicated loads without branches, so that a warp keeps 16
+   // of them in flight instead of paying one memory latency per column.
+   const bool fused = t.gsrc[0] || t.gsrc[1];
+   int fir[2][4], fic[2][8];
+   if (fused) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-         const int fc = T.fchild[2 * f + s];
-         if (fc < 0) continue;
-         fsrc[s] = T.C + T.coff[fc];
-         fld[s] = T.ldc[fc];
-         fmap[s] = T.pinv + T.pinvoff[2 * f + s];
 #pragma unroll
          for (int q = 0; q < 4; ++q) {
             const int r = i0 + lane + 32 * q;
-            fir[s][q] = (r >= n && r < m) ? fmap[s][r - n] : -1;
+            fir[s][q] = (t.gsrc[s] && r >= n && r < m) ? t.gmap[s][r - n] : -1;
+         }
+#pragma unroll
+         for (int u = 0; u < 8; ++u) {
+            const int c = j0 + warp * 8 + u;
+            fic[s][u] = (t.gsrc[s] && c >= n && c < m) ? t.gmap[s][c - n] : -1;
          }
       }
    }
-#pragma unroll 1
+#pragma unroll
    for (int cq = 0; cq < 8; cq += 4) {
       double v[4][4], d[4][4];
       double* gp[4];
@@ -428,18 +495,21 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
 #pragma unroll
          for (int q = 0; q < 4; ++q) v[u][q] = smem[(size_t)ct * GT_LDC + lane + 32 * q];
       }
+      if (fused) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-         if (!fsrc[s]) continue;
+         for (int s = 0; s < 2; ++s) {
+            if (!t.gsrc[s]) continue;
 #pragma unroll
-         for (int u = 0; u < 4; ++u) {
-            const int c = j0 + warp * 8 + cq + u;
-            const int ic = (c >= n && c < m) ? fmap[s][c - n] : -1;
-            if (ic < 0) continue;
-            const double* col = fsrc[s] + (size_t)ic * fld[s];
+            for (int u = 0; u < 4; ++u) {
+               const int ic = fic[s][cq + u];
+               const double* col = t.gsrc[s] + (size_t)max(ic, 0) * t.gld[s];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-               if (fir[s][q] >= ic) v[u][q] -= col[fir[s][q]];      // maps are increasing: row >= col
+               for (int q = 0; q < 4; ++q) {
+                  const bool hit = ic >= 0 && fir[s][q] >= ic;      // maps are increasing: row >= col
+                  const double gv = hit ? col[fir[s][q]] : 0.0;
+                  v[u][q] -= gv;
+               }
+            }
          }
       }
       if (op == 0) {
@@ -518,6 +588,8 @@ static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* 
    const int jend = min(k, w.y + 32);
    // cm is increasing: the chunk is skipped as a whole when it lies in the other part
    if (part == 0 ? (cm[w.y] >= pn) : (cm[jend - 1] < pn)) return;
+   const int sP = T.splitP ? T.splitP[p] : 1;
+   const int sQ = sP > 1 ? T.splitQ[p] : 0;
    // the contribution part of a fused child is gathered by the parent's DMMA epilogue
    if (part == 1 && T.fchild && (T.fchild[2 * p] == c || T.fchild[2 * p + 1] == c)) return;
    const double* src = T.C + T.coff[c];
@@ -529,6 +601,7 @@ static __global__ void __launch_bounds__(256) k_assemble(DevTree T, const int2* 
    for (int j = w.y + warp; j < jend; j += 8) {
       const int rj = cm[j];
       if ((rj < pn) != (part == 0)) continue;
+      if (sP > 1 && !split_owns(sP, sQ, pn, rj)) continue;      // another member's column
       const double* s = src + (size_t)j * ldcc;
       double* dcol = (rj < pn) ? PL + (size_t)rj * pldl : PC + (size_t)(rj - pn) * pldc - pn;
       int i = j + lane;
@@ -632,6 +705,117 @@ k_potrf_inv(DevTree T, const int* __restrict__ fronts, int step, int nb, double*
    for (int c = warp; c < wld; c += NW)
       for (int r = lane; r < wld; r += 32)
          Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? V[vpk<PW>(r, c)] : 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident 128 x 128 Cholesky + inverse (the block-column critical path of the large
+// fronts).  Same contract as k_potrf_inv<128>.  512 threads; thread (lane, warp) keeps the
+// elements (r = lane + 32 i, c = warp + 16 j), i < 4, j < 8 -- a 2-D cyclic layout, so the
+// shrinking trailing matrix stays spread over all warps.  One pass over k computes BOTH
+// factors by outer products with a single barrier per column:
+//     trailing matrix  A(r,c) -= L(r,k) L(c,k)             (c > k)
+//     inverse          T(r,c) -= L(r,k) V(k,c), V(k,:) = T(k,:) / L(k,k)   (c < k; T starts as I)
+// Column c of A is dead once it has been eliminated and column c of T is born at that very
+// step, so both live in the same 32 registers.  Shared memory only carries the broadcast of
+// column k of A and row k of T (double buffered, 4 KB).
+// ---------------------------------------------------------------------------
+constexpr int PR_THREADS = 512;
+static __global__ void __launch_bounds__(PR_THREADS, 1)
+k_potrf_inv_reg(DevTree T, const int* __restrict__ fronts, int step, int nb, double* __restrict__ W, int wld,
+                int* fail) {
+   __shared__ double cbuf[2][128];
+   __shared__ double vbuf[2][128];
+   const int f = fronts[blockIdx.x];
+   const int n = T.n[f], ldl = T.ldl[f];
+   const int p0 = step * nb;
+   const int pw = min(nb, n - p0);
+   double* A = T.L + T.loff[f] + (size_t)p0 * ldl + p0;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   double x[4][8];
+#pragma unroll
+   for (int j = 0; j < 8; ++j) {
+      const int c = warp + 16 * j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+         const int r = lane + 32 * i;
+         x[i][j] = (r < pw && c < pw && r >= c) ? A[(size_t)c * ldl + r] : (r == c ? 1.0 : 0.0);
+      }
+   }
+#pragma unroll
+   for (int jk = 0; jk < 8; ++jk) {
+      const int ik = jk >> 1;                    // k = 16 jk + kk lies in row block ik
+#pragma unroll 1
+      for (int kk = 0; kk < 16; ++kk) {
+         const int k = 16 * jk + kk;
+         if (k >= pw) break;
+         const int lk = k & 31;
+         double* cb = cbuf[k & 1];
+         double* vb = vbuf[k & 1];
+         if (warp == kk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cb[lane + 32 * i] = x[i][jk];
+         }
+         if (lane == lk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+               if (j < jk || (j == jk && warp < kk)) vb[warp + 16 * j] = x[ik][j];
+         }
+         __syncthreads();
+         const double akk = cb[k];
+         const bool ok = akk > 0.0;
+         if (!ok && threadIdx.x == 0) {
+            atomicExch(&fail[0], 1);
+            atomicMin(&fail[1], f);
+         }
+         const double rinv = ok ? rsqrt(akk) : 1.0;
+         double lr[4];
+#pragma unroll
+         for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            lr[i] = (i >= ik && r > k) ? cb[r] * rinv : 0.0;
+         }
+#pragma unroll
+         for (int j = 0; j < 8; ++j) {
+            const int c = warp + 16 * j;
+            if (j > jk || (j == jk && warp > kk)) {
+               // trailing matrix column c > k
+               const double lc = cb[c] * rinv;
+#pragma unroll
+               for (int i = 0; i < 4; ++i)
+                  if (i >= ik) x[i][j] -= lr[i] * lc;
+            } else if (j < jk || warp < kk) {
+               // inverse column c < k
+               const double vc = vb[c] * rinv;
+#pragma unroll
+               for (int i = 0; i < 4; ++i)
+                  if (i >= ik) x[i][j] -= lr[i] * vc;
+               if (lane == lk) x[ik][j] = vc;      // row k of the inverse is final
+            } else {
+               // c == k: column k of L is final (written out), column k of T is born
+#pragma unroll
+               for (int i = 0; i < 4; ++i) {
+                  const int r = lane + 32 * i;
+                  if (i >= ik) {
+                     if (r >= k && r < pw) A[(size_t)k * ldl + r] = (r == k) ? akk * rinv : lr[i];
+                     x[i][j] = (r == k) ? rinv : -lr[i] * rinv;
+                  } else {
+                     x[i][j] = 0.0;
+                  }
+               }
+            }
+         }
+      }
+   }
+   double* Wf = W + (size_t)blockIdx.x * wld * wld;
+#pragma unroll
+   for (int j = 0; j < 8; ++j) {
+      const int c = warp + 16 * j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+         const int r = lane + 32 * i;
+         if (r < wld && c < wld) Wf[r + (size_t)c * wld] = (r < pw && c < pw && r >= c) ? x[i][j] : 0.0;
+      }
+   }
 }
 
 }  // namespace sylver_b200

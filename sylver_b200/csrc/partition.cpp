@@ -111,9 +111,12 @@ struct Mapper {
 }  // namespace
 
 // owner[f] in [0, world) for every front.  world == 1 maps everything to rank 0.
-void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner) {
+void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner, std::vector<int>* grp0,
+                    std::vector<int>* grpn) {
    const int N = st.nnodes;
    owner.assign(N, 0);
+   if (grp0) grp0->assign(N, 0);
+   if (grpn) grpn->assign(N, 1);
    if (world <= 1 || N == 0) return;
    std::vector<double> wown(N), wsub(N);
    for (int f = 0; f < N; ++f) {
@@ -138,6 +141,15 @@ void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner) 
       mp.load[r] += wown[t.first];
    }
    for (int f = 0; f < N; ++f) owner[f] = own[f] < 0 ? 0 : own[f];
+   // rank group of every front: [owner, owner + 1) below the cut, the proportional-mapping
+   // group above it (the candidates for a front split over several GPUs)
+   if (grp0 && grpn) {
+      for (int f = 0; f < N; ++f) { (*grp0)[f] = owner[f]; (*grpn)[f] = 1; }
+      for (auto& t : mp.top) {
+         (*grp0)[t.first] = t.second.first;
+         (*grpn)[t.first] = t.second.second - t.second.first;
+      }
+   }
 }
 
 }  // namespace sylver_b200

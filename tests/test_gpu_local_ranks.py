@@ -143,3 +143,62 @@ def test_delays_cross_rank_boundaries(lib):
             assert rec == ref_rec, (world, rec, ref_rec)
             be = gen.backward_error(n, ptr, row, val, x, b)
             assert be <= 1e-14 and be <= 10 * max(be_ref, 1e-16), (world, be, be_ref)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("kind,k", [("lap27", 14), ("lap7", 20), ("lap27", 18)])
+def test_split_fronts_match_single_rank(lib, monkeypatch, kind, k, world):
+    """Top-of-tree fronts split over their rank group (block-column cyclic ownership, panel
+    broadcasts, contribution blocks gathered tile column by tile column -- SURVEY.md 8e).  The
+    threshold is lowered so that the small test trees have split fronts several levels deep,
+    including split children of split parents and groups of different sizes."""
+    sb.require_gpu()
+    single, (n, ptr, row, val, b) = _run(kind, k, True, 1)
+    ref_x = single[0][1]
+    be_ref = gen.backward_error(n, ptr, row, val, ref_x, b)
+    monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "40")
+    order = _problem(kind, k)[4]
+
+    def rank_body(rank, w):
+        s = sb.Solver()
+        assert s.analyse(n, ptr, row, order).flag == 0
+        inf = s.factorize(val, posdef=True)
+        info = s.split_info()
+        x = s.solve(b)
+        inf2 = s.factorize(val, posdef=True)
+        x2 = s.solve(b)
+        s.free()
+        return inf.flag, inf2.flag, info, x, x2
+
+    ranks = sb.run_local_ranks(world, rank_body)
+    assert ranks[0][2][0] >= 1, ranks[0][2]          # the plan really has split fronts
+    assert sum(r[2][1] for r in ranks) >= 2          # worked on by several ranks
+    assert sum(r[2][2] for r in ranks) >= 1          # and contribution pieces cross ranks
+    for flag, flag2, info, x, x2 in ranks:
+        assert flag == 0 and flag2 == 0
+        be = gen.backward_error(n, ptr, row, val, x, b)
+        assert be <= 1e-14 and be <= 10 * max(be_ref, 1e-16), (be, be_ref)
+        assert np.abs(x - ref_x).max() <= 1e-11 * max(1.0, np.abs(ref_x).max())
+        assert np.array_equal(x, x2)
+        assert np.array_equal(x, ranks[0][3])
+
+
+def test_split_front_not_posdef_is_reported(lib, monkeypatch):
+    """A non-positive pivot met inside a split front fails the factorization on every rank."""
+    sb.require_gpu()
+    n, ptr, row, val, order = _problem("lap27", 14)
+    monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "40")
+    bad = val.copy()
+    # the last pivot order position is in the root front: make its diagonal entry negative
+    col = int(np.argmax(order)) if order is not None else n - 1
+    bad[ptr[col] - 1] = -50.0
+
+    def rank_body(rank, w):
+        s = sb.Solver()
+        assert s.analyse(n, ptr, row, order).flag == 0
+        inf = s.factorize(bad, posdef=True)
+        s.free()
+        return inf.flag
+
+    flags = sb.run_local_ranks(2, rank_body)
+    assert all(f == -6 for f in flags), flags
