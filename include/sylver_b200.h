@@ -258,6 +258,14 @@ void sylver_b200_set_stream(void *cuda_stream, int enable);
  * (m-n)^2 (ld m-n); either may be NULL.  For indefinite trees _indef returns the number
  * of eliminated columns, D^-1 (2n doubles) and the pivot permutation (n ints, 1-based). */
 int sylver_b200_numeric_tree_get_front(void const *tree, int node, int *m, int *n, double *l, double *contrib);
+/* The engine works on a chain-coarsened copy of the assembly tree (a front that is its
+ * parent's last child is merged into it when that adds almost no explicit zeros; environment
+ * SYLVER_B200_AMALGAMATE=<fraction>, 0 disables, read at analyse).  `node` in the engine-level
+ * calls above counts ENGINE fronts.  This returns the number of reference fronts and the
+ * engine's structure: *nnodes fronts, rows / fully-summed columns / parent (0-based, *nnodes =
+ * virtual root) per engine front, and node_map[reference front] = engine front.  Borrowed. */
+int sylver_b200_symbolic_tree_view(void *symbolic_tree, int *nnodes, int const **nrow, int const **ncol,
+                                   int const **parent, int const **node_map);
 int sylver_b200_numeric_tree_get_front_indef(void const *tree, int node, int *nelim, double *d, int *perm);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch -------------------------

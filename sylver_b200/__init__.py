@@ -76,6 +76,7 @@ EXPORTS = [
     "spldlt_tree_solve_diag_bwd_dbl", "spldlt_tree_solve_fwd_posdef_dbl",
     "spldlt_tree_solve_bwd_posdef_dbl", "sylver_b200_device_count", "sylver_b200_version",
     "sylver_b200_akeep_view", "sylver_b200_symbolic_tree_cmap", "sylver_b200_numeric_tree_timings", "sylver_b200_numeric_tree_split_info",
+    "sylver_b200_symbolic_tree_view",
     "sylver_b200_fkeep_tree", "sylver_b200_factor_front_posdef", "sylver_b200_factor_front_indef",
     "sylver_b200_bench_dmma", "sylver_b200_bench_copy", "sylver_b200_akeep_tree",
     "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
@@ -137,6 +138,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_fkeep_tree.argtypes = [vp]
     L.sylver_b200_numeric_tree_timings.argtypes = [vp, dp]
     L.sylver_b200_numeric_tree_split_info.argtypes = [vp, vp]
+    L.sylver_b200_symbolic_tree_view.argtypes = [vp, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     L.sylver_b200_numeric_tree_get_front.argtypes = [vp, C.c_int, ip, ip, vp, vp]
     L.sylver_b200_factor_front_posdef.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                                   C.POINTER(C.c_float)]
@@ -365,6 +367,20 @@ class Solver:
         if not tree or self.L.sylver_b200_numeric_tree_timings(tree, out) != 0:
             return None
         return dict(device_s=out[0], h2d_s=out[1], wall_s=out[2], launches=int(out[3]))
+
+    def engine_tree(self):
+        """The chain-coarsened tree the engine factorizes: dict(nnodes, nrow, ncol, parent
+        (0-based, nnodes = virtual root), node_map (reference front -> engine front))."""
+        tree = self.L.sylver_b200_akeep_tree(self.akeep)
+        nn = C.c_int(0)
+        pr, pc, pp, pm = (C.POINTER(C.c_int)() for _ in range(4))
+        nref = self.L.sylver_b200_symbolic_tree_view(tree, C.byref(nn), C.byref(pr), C.byref(pc), C.byref(pp), C.byref(pm))
+        if nref < 0:
+            return None
+        g = nn.value
+        return dict(nnodes=g, nrow=np.ctypeslib.as_array(pr, (g,)).copy(), ncol=np.ctypeslib.as_array(pc, (g,)).copy(),
+                    parent=np.ctypeslib.as_array(pp, (g,)).copy(),
+                    node_map=np.ctypeslib.as_array(pm, (nref,)).copy() if nref else np.zeros(0, np.int32))
 
     def split_info(self):
         """(split fronts in the tree, split fronts this rank works on, pieces sent) of the last factorization."""

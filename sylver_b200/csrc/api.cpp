@@ -352,9 +352,21 @@ void* sylver_b200_akeep_tree(void* akeep) {
 int sylver_b200_symbolic_tree_cmap(void* symbolic_tree, long const** cptr, int const** cmap) {
    SymbolicTree* st = static_cast<SymbolicTree*>(symbolic_tree);
    if (!st) return -1;
-   *cptr = st->cmapoff.data();
-   *cmap = st->cmap.data();
+   *cptr = st->ref_cmapoff.data();      // maps of the reference structure (bit-exact output)
+   *cmap = st->ref_cmap.data();
    return 0;
+}
+
+int sylver_b200_symbolic_tree_view(void* symbolic_tree, int* nnodes, int const** nrow, int const** ncol,
+                                   int const** parent, int const** node_map) {
+   SymbolicTree* st = static_cast<SymbolicTree*>(symbolic_tree);
+   if (!st) return -1;
+   if (nnodes) *nnodes = st->nnodes;
+   if (nrow) *nrow = st->nrow.data();
+   if (ncol) *ncol = st->ncol.data();
+   if (parent) *parent = st->parent.data();
+   if (node_map) *node_map = st->node_map.data();
+   return st->ref_nnodes;
 }
 
 void* sylver_b200_fkeep_tree(void* fkeep) {
@@ -408,8 +420,10 @@ int sylver_b200_partition(void* akeep, int world, int* owner) {
    if (!ak || !ak->analysed || !ak->tree) return -1;
    std::vector<int> own;
    partition_tree(*ak->tree, world, own);
-   std::copy(own.begin(), own.end(), owner);
-   return (int)own.size();
+   // reported per REFERENCE node (the engine works on the chain-coarsened tree)
+   const SymbolicTree& st = *ak->tree;
+   for (int i = 0; i < st.ref_nnodes; ++i) owner[i] = own[st.node_map[i]];
+   return st.ref_nnodes;
 }
 
 int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* out) {
@@ -425,7 +439,8 @@ int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* o
       for (size_t l = 0; l < lists.size(); ++l)
          for (const Xfer& x : lists[l]) {
             if (4 * cnt + 3 < cap) {
-               out[4 * cnt] = (int)l; out[4 * cnt + 1] = x.f; out[4 * cnt + 2] = x.peer; out[4 * cnt + 3] = dir;
+               out[4 * cnt] = (int)l; out[4 * cnt + 1] = ak->tree->ref_top[x.f]; out[4 * cnt + 2] = x.peer;
+               out[4 * cnt + 3] = dir;
             }
             ++cnt;
          }

@@ -69,29 +69,195 @@ static SymbolicExtra& extras_of(const SymbolicTree* st) {
    return extras_map()[st];      // std::map references stay valid across other insertions
 }
 
+// ===========================================================================
+// Chain coarsening of the assembly tree (engine-internal; the analyse output is untouched).
+//
+// The reference's supernode rule (spral/src/core_analyse.f90:806-819) only merges a child
+// into its parent when the column counts nest exactly, so e.g. the separator planes of a
+// 7-point Laplacian arrive as chains of 25-100 thin fronts (n = one grid line, m = the whole
+// separator): every link rewrites a (m-n)^2 contribution block with a rank-n update -- the
+// DMMA tiles run at K = n and the tree gets hundreds of levels deep.  The engine merges a
+// front into its parent when the front is the parent's LAST child (their columns are then
+// adjacent in the pivot order) and the explicit zeros this adds to the child's columns (rows
+// of the parent the child does not have) stay below `tol` of the merged panel.  The merged
+// front factorizes the same matrix; the pivot order inside it is unchanged for the positive
+// definite path.  Node numbers of the coarse tree are what the engine-level calls use;
+// node_map gives reference node -> coarse node.
+// ===========================================================================
+namespace {
+struct CoarseTree {
+   int nnodes = 0;
+   std::vector<int> sptr, sparent, rlist, node_map;
+   std::vector<long> rptr, nptr, nlist;
+};
+
+bool coarsen_chains(int nnodes, const int* sptr, const int* sparent, const long* rptr, const int* rlist,
+                    const long* nptr, const long* nlist, double tol, CoarseTree& out) {
+   std::vector<int> first, last;      // groups of consecutive reference nodes [first, last]
+   out.node_map.assign(nnodes, 0);
+   for (int a = 0; a < nnodes;) {
+      int b = a;
+      long cur_n = sptr[a + 1] - sptr[a];
+      long cur_k = (rptr[a + 1] - rptr[a]) - cur_n;
+      while (b + 1 < nnodes && sparent[b] - 1 == b + 1) {
+         const int p = b + 1;
+         const long pm = rptr[p + 1] - rptr[p], pn = sptr[p + 1] - sptr[p];
+         if (pm < cur_k) return false;      // malformed structure
+         const double zeros = (double)cur_n * (double)(pm - cur_k);
+         const double panel = (double)(cur_n + pm) * (double)(cur_n + pn);
+         if (zeros > tol * panel) break;
+         cur_n += pn;
+         cur_k = pm - pn;
+         b = p;
+      }
+      for (int i = a; i <= b; ++i) out.node_map[i] = (int)first.size();
+      first.push_back(a);
+      last.push_back(b);
+      a = b + 1;
+   }
+   const int G = (int)first.size();
+   if (G == nnodes) return false;      // nothing merged: keep the arrays as given
+   out.nnodes = G;
+   out.sptr.resize(G + 1);
+   out.sparent.resize(G);
+   out.rptr.resize(G + 1);
+   out.nptr.resize(G + 1);
+   out.rptr[0] = 1;
+   out.nptr[0] = nptr[0];
+   const long nent = nptr[nnodes] - 1;
+   out.nlist.resize(2 * (size_t)nent);
+   for (int g = 0; g < G; ++g) {
+      const int a = first[g], b = last[g];
+      out.sptr[g] = sptr[a];
+      const int pb = sparent[b] - 1;
+      out.sparent[g] = (pb < nnodes ? out.node_map[pb] : G) + 1;
+      const int ncols = sptr[b + 1] - sptr[a];
+      const int nb_b = sptr[b + 1] - sptr[b];
+      const int* brows = rlist + (rptr[b] - 1) + nb_b;              // contribution rows of the top front
+      const int kb = (int)(rptr[b + 1] - rptr[b]) - nb_b;
+      for (int c = sptr[a]; c < sptr[b + 1]; ++c) out.rlist.push_back(c);
+      out.rlist.insert(out.rlist.end(), brows, brows + kb);
+      const long gm = ncols + kb;
+      out.rptr[g + 1] = out.rptr[g] + gm;
+      out.nptr[g + 1] = nptr[b + 1];
+      for (int j = a; j <= b; ++j) {
+         const long mj = rptr[j + 1] - rptr[j];
+         const int nj = sptr[j + 1] - sptr[j];
+         const int coff = sptr[j] - sptr[a];
+         const int* jr = rlist + (rptr[j] - 1);
+         for (long e = nptr[j] - 1; e < nptr[j + 1] - 1; ++e) {
+            const long dest = nlist[2 * e + 1] - 1;
+            const long col = dest / mj, row = dest - col * mj;
+            long nrow_new;
+            if (a == b) {
+               nrow_new = row;
+            } else if (row < nj) {
+               nrow_new = coff + row;
+            } else {
+               const int gidx = jr[row];                            // 1-based variable index
+               if (gidx < sptr[b + 1]) nrow_new = gidx - sptr[a];
+               else {
+                  const int* it = std::lower_bound(brows, brows + kb, gidx);
+                  if (it == brows + kb || *it != gidx) return false;
+                  nrow_new = ncols + (it - brows);
+               }
+            }
+            out.nlist[2 * e] = nlist[2 * e];
+            out.nlist[2 * e + 1] = (coff + col) * gm + nrow_new + 1;
+         }
+      }
+   }
+   out.sptr[G] = sptr[nnodes];
+   return true;
+}
+
+// per-edge assembly maps (two-pointer merge of sorted row lists); false on a malformed tree
+bool edge_maps(int nnodes, const std::vector<int>& nrow, const std::vector<int>& ncol, const std::vector<int>& parent,
+               const std::vector<long>& rptr0, const std::vector<int>& rlist, std::vector<long>& cmapoff,
+               std::vector<int>& cmap) {
+   cmapoff.assign(nnodes + 1, 0);
+   for (int i = 0; i < nnodes; ++i) cmapoff[i + 1] = cmapoff[i] + (nrow[i] - ncol[i]);
+   cmap.resize(cmapoff[nnodes]);
+   for (int c = 0; c < nnodes; ++c) {
+      const int p = parent[c];
+      const int k = nrow[c] - ncol[c];
+      if (k == 0) continue;
+      if (p >= nnodes) {   // root with a contribution: only legal for stand-alone dense fronts
+         for (int i = 0; i < k; ++i) cmap[cmapoff[c] + i] = -1;
+         continue;
+      }
+      const int* cr = &rlist[rptr0[c] + ncol[c]];
+      const int* pr = &rlist[rptr0[p]];
+      const int pm = nrow[p];
+      int q = 0;
+      for (int i = 0; i < k; ++i) {
+         while (q < pm && pr[q] < cr[i]) ++q;
+         if (q >= pm || pr[q] != cr[i]) return false;
+         cmap[cmapoff[c] + i] = q;
+      }
+   }
+   return true;
+}
+}  // namespace
+
 SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int* sparent,
                                    const long* rptr, const int* rlist, const long* nptr,
                                    const long* nlist, int* flag) {
    *flag = 0;
    SymbolicTree* st = new SymbolicTree();
    st->n = n;
+   // ---- outputs defined on the REFERENCE structure: flop count, assembly maps ----
+   st->ref_nnodes = nnodes;
+   {
+      std::vector<int> rn(nnodes), rc(nnodes), rp(nnodes);
+      std::vector<long> r0(nnodes + 1);
+      long flops = 0;
+      for (int i = 0; i <= nnodes; ++i) r0[i] = rptr[i] - 1;
+      for (int i = 0; i < nnodes; ++i) {
+         rn[i] = (int)(rptr[i + 1] - rptr[i]);
+         rc[i] = sptr[i + 1] - sptr[i];
+         rp[i] = std::min(sparent[i] - 1, nnodes);
+         if (rp[i] <= i) { *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr; }
+         const long mm = rn[i] - rc[i];
+         for (long j = 1; j <= rc[i]; ++j) flops += (mm + j) * (mm + j);
+         st->ref_maxfront = std::max(st->ref_maxfront, rn[i]);
+      }
+      st->num_flops = flops;
+      std::vector<int> rl(rlist, rlist + r0[nnodes]);
+      if (!edge_maps(nnodes, rn, rc, rp, r0, rl, st->ref_cmapoff, st->ref_cmap)) {
+         *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr;
+      }
+   }
+   // ---- engine structure: chains coarsened (SYLVER_B200_AMALGAMATE=<tol>, 0 disables) ----
+   CoarseTree ct;
+   {
+      const char* ae = getenv("SYLVER_B200_AMALGAMATE");
+      const double tol = ae ? atof(ae) : 0.02;
+      if (tol > 0 && nnodes > 1 && coarsen_chains(nnodes, sptr, sparent, rptr, rlist, nptr, nlist, tol, ct)) {
+         st->node_map = ct.node_map;
+         nnodes = ct.nnodes;
+         sptr = ct.sptr.data(); sparent = ct.sparent.data(); rptr = ct.rptr.data(); rlist = ct.rlist.data();
+         nptr = ct.nptr.data(); nlist = ct.nlist.data();
+      } else {
+         st->node_map.resize(nnodes);
+         for (int i = 0; i < nnodes; ++i) st->node_map[i] = i;
+      }
+   }
    st->nnodes = nnodes;
+   st->ref_top.assign(nnodes, 0);
+   for (int i = 0; i < st->ref_nnodes; ++i) st->ref_top[st->node_map[i]] = i;
    st->nrow.resize(nnodes); st->ncol.resize(nnodes); st->parent.resize(nnodes);
    st->nchild.assign(nnodes + 1, 0); st->level.assign(nnodes + 1, 0);
    st->rptr.resize(nnodes + 1);
    for (int i = 0; i <= nnodes; ++i) st->rptr[i] = rptr[i] - 1;
    st->rlist.assign(rlist, rlist + st->rptr[nnodes]);
-   long flops = 0;
    for (int i = 0; i < nnodes; ++i) {
       st->nrow[i] = (int)(rptr[i + 1] - rptr[i]);
       st->ncol[i] = sptr[i + 1] - sptr[i];
       st->parent[i] = std::min(sparent[i] - 1, nnodes);
       if (st->parent[i] <= i) { *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr; }
       st->nchild[st->parent[i]]++;
-      long mm = st->nrow[i] - st->ncol[i];
-      for (long j = 1; j <= st->ncol[i]; ++j) flops += (mm + j) * (mm + j);
    }
-   st->num_flops = flops;
    // children lists, decreasing node index (reference src/SymbolicTree.cxx:51-55)
    st->child_ptr.assign(nnodes + 2, 0);
    for (int i = 0; i <= nnodes; ++i) st->child_ptr[i + 1] = st->child_ptr[i] + st->nchild[i];
@@ -100,27 +266,8 @@ SymbolicTree* symbolic_tree_create(int n, int nnodes, const int* sptr, const int
       std::vector<int> fill(st->child_ptr.begin(), st->child_ptr.end() - 1);
       for (int i = nnodes - 1; i >= 0; --i) st->child_list[fill[st->parent[i]]++] = i;
    }
-   // per-edge assembly maps (two-pointer merge of sorted row lists)
-   st->cmapoff.assign(nnodes + 1, 0);
-   for (int i = 0; i < nnodes; ++i) st->cmapoff[i + 1] = st->cmapoff[i] + (st->nrow[i] - st->ncol[i]);
-   st->cmap.resize(st->cmapoff[nnodes]);
-   for (int c = 0; c < nnodes; ++c) {
-      const int p = st->parent[c];
-      const int k = st->nrow[c] - st->ncol[c];
-      if (k == 0) continue;
-      if (p >= nnodes) {   // root with a contribution: only legal for stand-alone dense fronts
-         for (int i = 0; i < k; ++i) st->cmap[st->cmapoff[c] + i] = -1;
-         continue;
-      }
-      const int* cr = &st->rlist[st->rptr[c] + st->ncol[c]];
-      const int* pr = &st->rlist[st->rptr[p]];
-      const int pm = st->nrow[p];
-      int q = 0;
-      for (int i = 0; i < k; ++i) {
-         while (q < pm && pr[q] < cr[i]) ++q;
-         if (q >= pm || pr[q] != cr[i]) { *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr; }
-         st->cmap[st->cmapoff[c] + i] = q;
-      }
+   if (!edge_maps(nnodes, st->nrow, st->ncol, st->parent, st->rptr, st->rlist, st->cmapoff, st->cmap)) {
+      *flag = SYLVER_ERROR_UNKNOWN; delete st; return nullptr;
    }
    // fused extend-add: the two children with the largest generated elements of every front
    st->fchild.assign(2 * (size_t)nnodes, -1);

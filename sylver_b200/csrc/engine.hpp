@@ -32,6 +32,12 @@ struct SymbolicTree {
    std::vector<long> pinvoff;                // [2*nnodes]
    std::vector<int> pinv;
    int nlevels = 0;
+   // ---- the reference structure as given at the seam (before chain coarsening) ----
+   int ref_nnodes = 0, ref_maxfront = 0;
+   std::vector<int> node_map;                // reference node -> engine (coarse) node
+   std::vector<int> ref_top;                 // engine node -> its topmost reference node
+   std::vector<long> ref_cmapoff;            // assembly maps of the reference structure
+   std::vector<int> ref_cmap;
    // ---- device resident static data ----
    int* d_rlist = nullptr;
    long* d_rptr = nullptr;       // 1-based values as given (nnodes+1)

@@ -350,16 +350,23 @@ static __global__ void __launch_bounds__(AP_THREADS) k_finish32(DevTree T, TileB
       if (threadIdx.x < 2 * npass) D[threadIdx.x] = dinv[threadIdx.x];
       return;
    }
-   // ---- rows p0..p0+wb of the columns left of the block (apply_rperm; both panels): the
-   // row chunks share the 2*p0 columns between them ----
-   for (int c = (chunk - 1) * AP_THREADS + threadIdx.x; c < 2 * p0; c += (nchunks - 1) * AP_THREADS) {
-      double* col = (c < p0 ? Lf + (size_t)c * ldl : Wf + (size_t)(c - p0) * ldl) + p0;
-      double v[IB];
-#pragma unroll
-      for (int i = 0; i < IB; ++i) v[i] = (i < wb) ? col[lperm[i]] : 0.0;
-#pragma unroll
-      for (int i = 0; i < IB; ++i)
-         if (i < wb) col[i] = v[i];
+   // ---- rows p0..p0+wb of the L columns left of the block (apply_rperm): one warp per column,
+   // one lane per row (a 256 B segment read and written once), shared between the row chunks.
+   // Skipped when the block needed no permutation.  The W panel is NOT permuted: its rows in the
+   // candidate range are dead once the block column's own trailing update has been applied
+   // (later updates read only their own block's W columns, the contribution update rows >= n).
+   {
+      const int lane = threadIdx.x & 31;
+      const int src = (lane < wb) ? lperm[lane] : lane;
+      if (__any_sync(0xffffffffu, src != lane)) {
+         const int nw = AP_THREADS / 32;
+         for (int c = (chunk - 1) * nw + (threadIdx.x >> 5); c < p0; c += (nchunks - 1) * nw) {
+            double* col = Lf + (size_t)c * ldl + p0;
+            const double v = (lane < wb) ? col[src] : 0.0;
+            __syncwarp();
+            if (lane < wb) col[lane] = v;
+         }
+      }
    }
    const int r = p0 + wb + (chunk - 1) * AP_THREADS + threadIdx.x;
    if (r >= m) return;
@@ -390,8 +397,10 @@ static __global__ void __launch_bounds__(AP_THREADS) k_finish32(DevTree T, TileB
 // `nleft` columns wide: lower-triangle panel L (all columns < n) and the rows of W in
 // the eliminated columns (swap_cols, ldlt_tpp.cxx:44-72).  Called by a whole CTA.
 // ---------------------------------------------------------------------------
+// W rows are only swapped in the columns [wfirst, nleft): the pivots whose trailing update is
+// still to come (older W columns are dead in the candidate row range).
 __device__ __forceinline__ void cta_sym_swap(double* Lf, double* Wf, int* perm, int ldl, int m, int n, int nleft,
-                                             int i, int j) {
+                                             int i, int j, int wfirst) {
    if (i == j) return;
    if (i > j) { const int x = i; i = j; j = x; }
    const int tid = threadIdx.x, nt = blockDim.x;
@@ -399,7 +408,7 @@ __device__ __forceinline__ void cta_sym_swap(double* Lf, double* Wf, int* perm, 
    for (int c = tid; c < i; c += nt) {
       double* col = Lf + (size_t)c * ldl;
       const double x = col[i]; col[i] = col[j]; col[j] = x;
-      if (c < nleft) {
+      if (c < nleft && c >= wfirst) {
          double* wc = Wf + (size_t)c * ldl;
          const double y = wc[i]; wc[i] = wc[j]; wc[j] = y;
       }
@@ -453,7 +462,7 @@ static __global__ void __launch_bounds__(SW_THREADS) k_swap_failed(DevTree T, co
       double* Lf = T.L + T.loff[f];
       double* Wf = T.W + T.woff[f];
       int* perm = T.perm + T.permoff[f];
-      for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0 + npass, p0 + npass + i, na - ns + i);
+      for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0 + npass, p0 + npass + i, na - ns + i, p0);
    }
    if (threadIdx.x == 0) {
       st.kbeg = p0;
@@ -585,7 +594,7 @@ static __global__ void __launch_bounds__(TPP_THREADS) k_tpp(DevTree T, const int
       bool done = false;
       for (p = nelim + 1; p < n; ++p) {
          if (col_small(p)) {
-            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, p);
+            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, p, nelim);
             zero_pivot();
             done = true;
             break;
@@ -630,15 +639,15 @@ static __global__ void __launch_bounds__(TPP_THREADS) k_tpp(DevTree T, const int
          }
          __syncthreads();
          if (ok2) {
-            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, t);
-            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim + 1, p);
+            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, t, nelim);
+            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim + 1, p, nelim);
             elim_2x2(d11, d21, d22);
             done = true;
             break;
          }
          maxp = fmax(maxp, fabs(a21));
          if (fabs(a22) >= u * maxp) {
-            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, p);
+            cta_sym_swap(Lf, Wf, perm, ldl, m, n, nelim, nelim, p, nelim);
             elim_1x1();
             done = true;
             break;

@@ -85,12 +85,12 @@ def _cross_rank_delays(n, ptr, row, val, order, worlds):
     s = sb.Solver()
     assert s.analyse(n, ptr, row, order).flag == 0
     s.factorize(val, posdef=False)
-    sym = s.symbolic()
     L = sb.lib()
     tree = L.sylver_b200_fkeep_tree(s.fkeep)
-    nn = sym["nnodes"]
-    ncol = np.diff(sym["sptr"])
-    parent = sym["sparent"] - 1
+    et = s.engine_tree()                   # the engine's (chain-coarsened) fronts
+    nn, ncol, parent = et["nnodes"], et["ncol"], et["parent"]
+    top = np.zeros(nn, dtype=np.int64)     # engine front -> its topmost reference front
+    top[et["node_map"]] = np.arange(len(et["node_map"]))
     delayed = np.zeros(nn, dtype=bool)
     ndin = np.zeros(nn + 1, dtype=np.int64)
     for f in range(nn):
@@ -102,7 +102,7 @@ def _cross_rank_delays(n, ptr, row, val, order, worlds):
     inner = parent < nn
     hit = []
     for world in worlds:
-        own = sb.partition(s, world)
+        own = sb.partition(s, world)[top]
         if (delayed & inner & (own != own[np.minimum(parent, nn - 1)])).any():
             hit.append(world)
     s.free()
