@@ -308,7 +308,16 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          geo.push_back(GeoUpd{f, nt->m[f], nt->n[f], nt->ldl[f], nt->loff[f], nt->woff[f], nt->doff[f], nt->permoff[f]});
       }
       // work lists (prefix sums are nested: step s uses the first cnt_s fronts of `order`)
-      std::vector<int> row_prefix(cnt + 1), upd_prefix(cnt + 1), con_prefix(cnt + 1);
+      std::vector<int> row_prefix(cnt + 1), upd_prefix(cnt + 1), con_prefix(cnt + 1), inn_prefix(cnt + 1);
+      {
+         int a3 = 0;
+         for (int i = 0; i < cnt; ++i) {
+            // block column -> rest of its outer panel: at most two tile columns
+            inn_prefix[i] = a3;
+            a3 += 2 * ((nt->m[order[i]] + GT_BM - 1) / GT_BM + 1);
+         }
+         inn_prefix[cnt] = a3;
+      }
       {
          int a0 = 0, a1 = 0, a2 = 0;
          for (int i = 0; i < cnt; ++i) {
@@ -342,7 +351,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       Packer pk;
       const size_t o_geo = pk.put(geo), o_order = pk.put(order), o_row = pk.put(row_prefix),
                    o_upd = pk.put(upd_prefix), o_con = pk.put(con_prefix), o_asm = pk.put(asmw),
-                   o_del = pk.put(delay_work), o_slot = pk.put(slot);
+                   o_del = pk.put(delay_work), o_slot = pk.put(slot), o_inn = pk.put(inn_prefix);
       // ---- device buffers for the level ----
       {
          if ((size_t)gcnt > nt->lvl_out_cap) {
@@ -375,6 +384,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       const int2* d_asm = reinterpret_cast<const int2*>(dl + o_asm);
       const int2* d_del = reinterpret_cast<const int2*>(dl + o_del);
       const int* d_slot = reinterpret_cast<const int*>(dl + o_slot);
+      const int* d_inn = reinterpret_cast<const int*>(dl + o_inn);
       DiagScratch* d_diag = static_cast<DiagScratch*>(nt->d_diag);
       k_set_geometry<<<((int)geo.size() + 255) / 256, 256, 0, s>>>(d_geo, (int)geo.size(), nt->d_m, nt->d_n, nt->d_ldl,
                                                                    nt->d_loff, nt->d_woff, nt->d_doff, nt->d_permoff);
@@ -405,31 +415,54 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
             k_assemble_delays<<<(int)delay_work.size(), 256, 0, s>>>(T, d_del);
             ++launches;
          }
-         // ---- APTP block columns ----
-         const int nsteps = (maxn + IB - 1) / IB;
-         int cnt_s = cnt;
-         for (int sidx = 0; sidx < nsteps; ++sidx) {
-            while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= sidx * IB) --cnt_s;
-            if (cnt_s == 0) break;
-            TileBatch rb{d_fr, d_row, cnt_s};
-            TileBatch ub{d_fr, d_upd, cnt_s};
-            {
-               ProfScope ps(nt, KC_POTRF);
-               k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
-               k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
-               k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
-               k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
-               launches += 4;
+         // ---- APTP, two-level blocking: outer panels of OB candidates, IB-wide block columns
+         // inside.  After o panels a front has max(0, n - o*OB) active candidates left and inside
+         // a panel every block column consumes IB of them (passed or failed), so the launch
+         // sequence is known to the host although the outcome of the pivoting is not.
+         const int nouter = (maxn + OB - 1) / OB;
+         int cnt_o = cnt;
+         for (int o = 0; o < nouter; ++o) {
+            while (cnt_o > 0 && nt->n[order[cnt_o - 1]] <= o * OB) --cnt_o;
+            if (cnt_o == 0) break;
+            k_outer_begin<<<(cnt_o + 127) / 128, 128, 0, s>>>(T, d_fr, cnt_o);
+            ++launches;
+            int cnt_s = cnt_o;
+            for (int ib = 0; ib < OB / IB; ++ib) {
+               while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= o * OB + ib * IB) --cnt_s;
+               if (cnt_s == 0) break;
+               TileBatch rb{d_fr, d_row, cnt_s};
+               TileBatch ub{d_fr, d_inn, cnt_s};
+               {
+                  ProfScope ps(nt, KC_POTRF);
+                  k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
+                  k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
+                  k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
+                  k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
+                  launches += 4;
+               }
+               {
+                  // rest of the panel, including the columns that just failed (CTAs of fronts
+                  // with nothing left in the panel exit at once)
+                  ProfScope ps(nt, KC_TRSM);
+                  k_gemm_batched<<<inn_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
+                  ++launches;
+               }
             }
-            {
+            if (nt->n[order[0]] > (o + 1) * OB || o > 0) {
+               // columns behind the panel exist (more candidates, or failed columns of earlier panels)
+               TileBatch ub{d_fr, d_upd, cnt_o};
                ProfScope ps(nt, KC_UPDATE);
-               k_gemm_batched<<<upd_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
+               k_gemm_batched<<<upd_prefix[cnt_o], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 5, 0, IB, nullptr, 0, 0, 1);
+               k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr);
+               launches += 2;
+            } else {
+               k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr);
                ++launches;
             }
          }
          // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
          {
-            ProfScope ps(nt, KC_TRSM);
+            ProfScope ps(nt, KC_ZERO);
             k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
             ++launches;
          }

@@ -26,6 +26,13 @@ struct FrontState {
    int wb;       // width of the current block
    int nelim1;   // eliminated by the first (APTP) pass
    int nelim;    // eliminated in total; n - nelim columns are delayed to the parent
+   // two-level blocking: the candidates are processed in outer panels of up to 128 columns;
+   // inside a panel the 32-wide block columns update only the panel, the rest of the front
+   // gets one rank-(p0 - obeg) update per panel
+   int obeg;     // first column eliminated by the current outer panel
+   int oend;     // end of the current outer panel (<= na)
+   int pa;       // end of the panel's active candidates; [pa, oend) failed inside this panel
+   int pad;
 };
 
 // Device view of the assembly tree (structure-of-arrays, one entry per front).
@@ -362,14 +369,17 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    if (mode >= 3) {
       // ---- indefinite path: operands are W = L*D (A side) and L (B side); the extent of the
       // update is read from the device-resident front state (nothing here is known to the host)
+      // mode 3: block column [kbeg, kbeg+klen) -> the rest of the current outer panel
+      // mode 5: outer panel [obeg, p0) -> everything behind the panel
+      // mode 4: all eliminated columns -> contribution block
       const FrontState st = T.state[f];
       const double* Wf = T.W + T.woff[f];
-      const int kbeg = (mode == 3) ? st.kbeg : 0;
-      t.K = (mode == 3) ? st.klen : st.nelim;
-      if (mode == 3 && t.K == 0) return;
-      const int first = (mode == 3) ? st.p0 : n;     // first column/row of the updated region
+      const int kbeg = (mode == 3) ? st.kbeg : (mode == 5 ? st.obeg : 0);
+      t.K = (mode == 3) ? st.klen : (mode == 5 ? st.p0 - st.obeg : st.nelim);
+      if (mode != 4 && t.K == 0) return;
+      const int first = (mode == 3) ? st.p0 : (mode == 5 ? st.oend : n);     // first column/row of the updated region
       const int base = first & ~1;
-      const int cend = (mode == 3) ? n : m;
+      const int cend = (mode == 3) ? st.oend : (mode == 5 ? n : m);
       if (cend <= first) return;
       const int TR = (m - base + GT_BM - 1) / GT_BM;
       const int TC = (cend - base + GT_BN - 1) / GT_BN;
@@ -384,8 +394,8 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       t.lda = t.ldb = ldl;
       t.arows = min(GT_BM, m - i0);
       t.brows = min(GT_BN, m - j0);
-      if (mode == 3) {
-         dbase = Lf; ldd = ldl; clo = first; chi = n; rmin = 0; lower = true; op = 0;
+      if (mode != 4) {
+         dbase = Lf; ldd = ldl; clo = first; chi = cend; rmin = 0; lower = true; op = 0;
          t.prefetch = true;
       } else {
          const int ldc = T.ldc[f];

@@ -52,7 +52,7 @@ static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int*
    const int f = fronts[blockIdx.x];
    FrontState& st = T.state[f];
    const int p0 = st.p0;
-   const int wb = min(IB, st.na - p0);
+   const int wb = min(IB, st.pa - p0);
    const int lane = threadIdx.x;
    if (lane == 0) st.wb = wb;
    if (wb <= 0) return;
@@ -451,10 +451,10 @@ static __global__ void __launch_bounds__(SW_THREADS) k_swap_failed(DevTree T, co
       if (threadIdx.x == 0) st.klen = 0;
       return;
    }
-   const int p0 = st.p0, na = st.na;
+   const int p0 = st.p0, pa = st.pa;
    const int npass = adjusted_pass(min(st.npass, wb), scratch[blockIdx.x].dinv);
    const int nf = wb - npass;
-   const int q = na - p0 - wb;
+   const int q = pa - p0 - wb;
    const int ns = min(nf, q);
    __syncthreads();
    if (ns > 0) {
@@ -462,15 +462,50 @@ static __global__ void __launch_bounds__(SW_THREADS) k_swap_failed(DevTree T, co
       double* Lf = T.L + T.loff[f];
       double* Wf = T.W + T.woff[f];
       int* perm = T.perm + T.permoff[f];
-      for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0 + npass, p0 + npass + i, na - ns + i, p0);
+      for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0 + npass, p0 + npass + i, pa - ns + i, p0);
    }
    if (threadIdx.x == 0) {
       st.kbeg = p0;
       st.klen = npass;
       st.p0 = p0 + npass;
-      st.na = na - nf;
+      st.pa = pa - nf;       // failed columns stay inside the outer panel (they keep receiving its updates)
       st.npass = IB;
       st.wb = 0;
+   }
+}
+
+// Outer panel of the two-level blocking: up to OB candidates.
+constexpr int OB = 128;
+static __global__ void k_outer_begin(DevTree T, const int* __restrict__ fronts, int cnt) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= cnt) return;
+   FrontState& st = T.state[fronts[i]];
+   st.obeg = st.p0;
+   st.oend = min(st.p0 + OB, st.na);
+   st.pa = st.oend;
+}
+// After the panel's rank-(p0 - obeg) update of the columns behind it, every column >= p0 has
+// seen the same pivots: the panel's failed columns [p0, oend) move behind the still-active
+// candidates (one CTA per front).
+static __global__ void __launch_bounds__(SW_THREADS) k_outer_end(DevTree T, const int* __restrict__ fronts) {
+   const int f = fronts[blockIdx.x];
+   FrontState& st = T.state[f];
+   const int p0 = st.p0, na = st.na, oend = st.oend;
+   const int nf = oend - p0;
+   if (nf <= 0) return;
+   const int ns = min(nf, na - oend);
+   __syncthreads();
+   if (ns > 0) {
+      const int m = T.m[f], n = T.n[f], ldl = T.ldl[f];
+      double* Lf = T.L + T.loff[f];
+      double* Wf = T.W + T.woff[f];
+      int* perm = T.perm + T.permoff[f];
+      for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0, p0 + i, na - ns + i, p0);
+   }
+   if (threadIdx.x == 0) {
+      st.na = na - nf;
+      st.oend = p0;
+      st.pa = p0;
    }
 }
 
@@ -721,6 +756,7 @@ static __global__ void __launch_bounds__(256) k_init_front(DevTree T, const int*
    if (threadIdx.x == 0) {
       FrontState s;
       s.p0 = 0; s.na = T.n[f]; s.npass = IB; s.kbeg = 0; s.klen = 0; s.wb = 0; s.nelim1 = 0; s.nelim = 0;
+      s.obeg = 0; s.oend = 0; s.pa = 0; s.pad = 0;
       T.state[f] = s;
    }
 }
