@@ -231,6 +231,11 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    const bool tpp_everywhere = (nt->opt.failed_pivot_method != 2) || (nt->opt.pivot_method == 3);
    const bool multi = nt->world > 1;
    const int me = nt->rank;
+   int OB = OB_DEFAULT;
+   {
+      const char* oe = getenv("SYLVER_B200_OB");
+      if (oe && atoi(oe) >= IB) OB = atoi(oe) / IB * IB;
+   }
    long launches = 0;
    for (auto& c : nt->chunks) c.used = 0;
    if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
@@ -312,9 +317,9 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       {
          int a3 = 0;
          for (int i = 0; i < cnt; ++i) {
-            // block column -> rest of its outer panel: at most two tile columns
+            // block column -> rest of its outer panel: at most OB / 128 + 1 tile columns
             inn_prefix[i] = a3;
-            a3 += 2 * ((nt->m[order[i]] + GT_BM - 1) / GT_BM + 1);
+            a3 += (OB / GT_BN + 1) * ((nt->m[order[i]] + GT_BM - 1) / GT_BM + 1);
          }
          inn_prefix[cnt] = a3;
       }
@@ -424,7 +429,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          for (int o = 0; o < nouter; ++o) {
             while (cnt_o > 0 && nt->n[order[cnt_o - 1]] <= o * OB) --cnt_o;
             if (cnt_o == 0) break;
-            k_outer_begin<<<(cnt_o + 127) / 128, 128, 0, s>>>(T, d_fr, cnt_o);
+            k_outer_begin<<<(cnt_o + 127) / 128, 128, 0, s>>>(T, d_fr, cnt_o, OB);
             ++launches;
             int cnt_s = cnt_o;
             for (int ib = 0; ib < OB / IB; ++ib) {

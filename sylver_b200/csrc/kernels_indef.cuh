@@ -59,10 +59,15 @@ static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int*
    const int ldl = T.ldl[f];
    const double* A = T.L + T.loff[f] + (size_t)p0 * ldl + p0;
    // load (full symmetric storage)
+   // coalesced reads of the lower triangle, mirrored through shared memory
+#pragma unroll
    for (int c = 0; c < IB; ++c) {
       double v = 0.0;
-      if (lane < wb && c < wb) v = (lane >= c) ? A[(size_t)c * ldl + lane] : A[(size_t)lane * ldl + c];
-      S[lane * SLD + c] = v;
+      if (lane < wb && c < wb && lane >= c) v = A[(size_t)c * ldl + lane];
+      if (lane >= c) {
+         S[lane * SLD + c] = v;
+         S[c * SLD + lane] = v;
+      }
    }
    lperm[lane] = lane;
    dinv[2 * lane] = 0.0;
@@ -182,7 +187,8 @@ static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int*
    }
    __syncwarp();
    DiagScratch& o = scratch[blockIdx.x];
-   for (int c = 0; c < IB; ++c) o.S[lane * SLD + c] = S[lane * SLD + c];
+#pragma unroll
+   for (int r = 0; r < IB; ++r) o.S[r * SLD + lane] = S[r * SLD + lane];      // coalesced
    o.dinv[2 * lane] = dinv[2 * lane];
    o.dinv[2 * lane + 1] = dinv[2 * lane + 1];
    if (lane < 2) o.dinv[2 * IB + lane] = 0.0;
@@ -475,8 +481,8 @@ static __global__ void __launch_bounds__(SW_THREADS) k_swap_failed(DevTree T, co
 }
 
 // Outer panel of the two-level blocking: up to OB candidates.
-constexpr int OB = 128;
-static __global__ void k_outer_begin(DevTree T, const int* __restrict__ fronts, int cnt) {
+constexpr int OB_DEFAULT = 256;      // SYLVER_B200_OB overrides (multiple of 32)
+static __global__ void k_outer_begin(DevTree T, const int* __restrict__ fronts, int cnt, int OB) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= cnt) return;
    FrontState& st = T.state[fronts[i]];
