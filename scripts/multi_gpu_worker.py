@@ -22,14 +22,20 @@ from sylver_b200 import gen
 def main():
     kind, k = sys.argv[1], int(sys.argv[2])
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    posdef = not (len(sys.argv) > 4 and sys.argv[4] == "indef")      # "indef": APTP LDL^T on the same matrix
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     sb.comm_init_from_torch(dist, local)
-    n, ptr, row, val = (gen.laplacian_27pt if kind == "lap27" else gen.laplacian_7pt)(k)
-    order = gen.nested_dissection_order(k)
+    if kind == "kkt":
+        n, ptr, row, val = gen.stokes_kkt(k)
+        order = gen.nested_dissection_order(k, dofs_per_cell=4)
+        posdef = False
+    else:
+        n, ptr, row, val = (gen.laplacian_27pt if kind == "lap27" else gen.laplacian_7pt)(k)
+        order = gen.nested_dissection_order(k)
     s = sb.Solver()
     inf = s.analyse(n, ptr, row, order)
     assert inf.flag == 0
@@ -38,7 +44,7 @@ def main():
     for r in range(reps):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        inf = s.factorize(val, posdef=True)
+        inf = s.factorize(val, posdef=posdef)
         torch.cuda.synchronize(); dist.barrier()
         times.append(time.perf_counter() - t0)
         assert inf.flag == 0, inf.flag
@@ -47,13 +53,16 @@ def main():
     be = gen.backward_error(n, ptr, row, val, x, b)
     # partial solves: forward then backward must compose to the same solution on every rank
     y = s.solve(b, job=1)
+    if not posdef:
+        y = s.solve(y, job=2)
     y = s.solve(y, job=3)
     agree = float(np.abs(y - x).max())
     tm = s.timings()
     allt = [None] * world
     dist.all_gather_object(allt, tm["device_s"])
     if rank == 0:
-        print(json.dumps(dict(kind=kind, k=k, world=world, n=n, num_flops=flops, wall_s=min(times),
+        print(json.dumps(dict(kind=kind, k=k, posdef=posdef, world=world, n=n, num_flops=flops, wall_s=min(times),
+                              num_neg=inf.num_neg, num_delay=inf.num_delay, split=s.split_info(),
                               gflops=flops / min(times) / 1e9, device_s_per_rank=allt, bwderr=be,
                               fwd_bwd_vs_full=agree, launches=tm["launches"])), flush=True)
     assert be <= 1e-14, be

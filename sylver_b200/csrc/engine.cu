@@ -674,6 +674,35 @@ static void build_posdef_plan(NumericTree* nt) {
          }
          prefix.push_back(acc);
          ls.updr_tiles = acc;
+         // paired updates: the first two tile columns (the next pair of block columns) / the rest
+         ls.upd2n_prefix = prefix.size();
+         acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int base = p0 + std::min(nb, nt->n[f] - p0);
+            prefix.push_back(acc);
+            if (nt->n[f] > base) {
+               const int TR = (nt->m[f] - base + GT_BM - 1) / GT_BM;
+               const int TC = (nt->n[f] - base + GT_BN - 1) / GT_BN;
+               for (int tj = 0; tj < std::min(TC, 2); ++tj) acc += TR - tj;
+            }
+         }
+         prefix.push_back(acc);
+         ls.upd2n_tiles = acc;
+         ls.upd2r_prefix = prefix.size();
+         acc = 0;
+         for (int i = 0; i < cnt; ++i) {
+            const int f = fr[i];
+            const int base = p0 + std::min(nb, nt->n[f] - p0);
+            prefix.push_back(acc);
+            if (nt->n[f] > base) {
+               const int TR = (nt->m[f] - base + GT_BM - 1) / GT_BM;
+               const int TC = (nt->n[f] - base + GT_BN - 1) / GT_BN;
+               for (int tj = 2; tj < TC; ++tj) acc += TR - tj;
+            }
+         }
+         prefix.push_back(acc);
+         ls.upd2r_tiles = acc;
       }
       // contribution tiles
       lp.contrib_prefix = prefix.size();
@@ -931,7 +960,47 @@ static void issue_posdef(NumericTree* nt) {
       // update, its diagonal-block factorization and panel solve run on a second stream beside
       // the rest of the trailing update, taking the latency-bound potrf off the critical path.
       const bool lookahead = nt->stream2 && lp.steps.size() >= 2 && lp.count <= 16;
-      if (!lookahead) {
+      if (nt->pair_updates) {
+         // Block columns are factorized in pairs: column si, a rank-nb update of column si+1
+         // alone, column si+1 -- then ONE rank-2nb update of everything behind the pair (half as
+         // many read-modify-write passes over the trailing panel and twice the work per tile).
+         // With look-ahead the next pair is factorized on the second stream as soon as its two
+         // tile columns have received the update, beside the rest of that update.
+         const size_t S = lp.steps.size();
+         auto upd = [&](const LevelStep& ls, size_t off, int tiles, int kstep, int knb, int tstart, cudaStream_t q) {
+            if (tiles == 0) return;
+            TileBatch b{d_fr, nt->d_prefix + off, ls.cnt};
+            ProfScope ps(nt, KC_UPDATE, q);
+            k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, kstep, knb, nullptr, 0, tstart, 1);
+            ++launches;
+         };
+         auto chain = [&](size_t si, cudaStream_t q) {
+            potrf(si, q);
+            trsm(si, q);
+            if (si + 1 < S) {
+               upd(lp.steps[si], lp.steps[si].updn_prefix, lp.steps[si].updn_tiles, (int)si, nb, 0, q);
+               potrf(si + 1, q);
+               trsm(si + 1, q);
+            }
+         };
+         chain(0, s);
+         for (size_t si = 0; si + 2 < S; si += 2) {
+            const LevelStep& l1 = lp.steps[si + 1];      // tile lists behind the pair (si, si+1)
+            if (!lookahead) {
+               upd(l1, l1.upd_prefix, l1.upd_tiles, (int)(si / 2), 2 * nb, 0, s);
+               chain(si + 2, s);
+            } else {
+               cudaStream_t s2 = nt->stream2;
+               upd(l1, l1.upd2n_prefix, l1.upd2n_tiles, (int)(si / 2), 2 * nb, 0, s);
+               CU_TRY(cudaEventRecord(nt->ev_next, s));
+               CU_TRY(cudaStreamWaitEvent(s2, nt->ev_next, 0));
+               chain(si + 2, s2);
+               CU_TRY(cudaEventRecord(nt->ev_panel, s2));
+               upd(l1, l1.upd2r_prefix, l1.upd2r_tiles, (int)(si / 2), 2 * nb, 2, s);
+               CU_TRY(cudaStreamWaitEvent(s, nt->ev_panel, 0));
+            }
+         }
+      } else if (!lookahead) {
          for (size_t si = 0; si < lp.steps.size(); ++si) {
             potrf(si, s);
             trsm(si, s);
@@ -1066,6 +1135,8 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       {
          const char* po = getenv("SYLVER_B200_POTRF_OLD");
          nt->potrf_old = po && po[0] == '1';
+         const char* pe = getenv("SYLVER_B200_PAIR");
+         nt->pair_updates = !(pe && pe[0] == '0');
       }
       {
          const char* la = getenv("SYLVER_B200_LOOKAHEAD");

@@ -108,6 +108,8 @@ struct LevelStep {
    size_t trsm_prefix, upd_prefix;   // offsets into d_prefix
    int updn_tiles = 0, updr_tiles = 0;      // look-ahead split: first tile column / the rest
    size_t updn_prefix = 0, updr_prefix = 0;
+   int upd2n_tiles = 0, upd2r_tiles = 0;    // paired (rank-2nb) updates: first two tile columns / the rest
+   size_t upd2n_prefix = 0, upd2r_prefix = 0;
 };
 struct LevelPlan {
    int first, count;               // range in level_nodes
@@ -163,6 +165,7 @@ struct NumericTree {
    cudaGraphExec_t graph = nullptr;
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
    bool profile = false;
+   bool pair_updates = true;             // SYLVER_B200_PAIR=0: one rank-nb trailing update per block column
    bool potrf_old = false;               // SYLVER_B200_POTRF_OLD=1: shared-memory k_potrf_inv<128> (A/B runs)
    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
    double prof_ms[KC_COUNT] = {0};
