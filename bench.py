@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=100, help="grid side of the 27-point Laplacian")
-    ap.add_argument("--sample-grid", type=int, default=44, help="grid side of the CPU sample")
+    ap.add_argument("--sample-grid", type=int, default=56, help="grid side of the CPU sample (56^3: ~4 s of CPU work per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -224,6 +224,7 @@ def ours(a):
             inf = s.factorize(dptr, posdef=True)
             assert inf.flag == 0, inf.flag
         launches_per_step = s.timings()["launches"]
+        split = s.split_info() or (0, 0, 0)
         clocks = ClockSampler(local)
         barrier(); torch.cuda.synchronize()
         clocks.start()
@@ -308,7 +309,7 @@ def ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = run_reference_sample(a.sample_grid, 2, 1)
+        r = run_reference_sample(a.sample_grid, 3, 1)
         if r is not None:
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
                    "sample": r["sample"]}
@@ -325,7 +326,8 @@ def ours(a):
                        "num_flops": num_flops, "order": "geometric nested dissection (input)",
                        "nemin": 32, "parallelism": "1 GPU" if world == 1 else
                        f"assembly tree partitioned over {world} GPUs (proportional mapping), contribution "
-                       f"blocks of cross-GPU edges by NCCL send/recv",
+                       f"blocks of cross-GPU edges by NCCL send/recv; {split[0]} top-of-tree fronts split "
+                       f"block-column-cyclic over their rank group (panel ncclBroadcast)",
                        "l2": "factor+contribution arenas (>20 GB) far exceed the 126 MB L2; no flush needed",
                        "analyse_s": t_analyse, "bwderr": bwderr},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(val.nbytes),
