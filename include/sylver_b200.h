@@ -298,6 +298,15 @@ int sylver_b200_partition(void *akeep, int world, int *owner);
 /* The contribution blocks rank `rank` sends/receives, as quadruples
  * (level, front, peer, dir: 0 send / 1 recv); returns their number (may exceed cap/4). */
 int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *out);
+/* Host-only (no GPU, no communicator): the positive definite multi-GPU plan of `rank` among
+ * `world` ranks, including the fronts split over rank groups (environment SYLVER_B200_SPLIT,
+ * SYLVER_B200_SPLIT_MIN as at factorization).  out8 = { split fronts in the tree, split fronts
+ * this rank works on, factor arena bytes, contribution arena bytes, panel staging bytes,
+ * contribution pieces sent, received, most point-to-point operations in one level }.  pieces
+ * receives 6 longs per piece while they fit in cap: level, front (topmost reference node), peer,
+ * offset and count (doubles, inside the front's contribution block), direction (0 send, 1
+ * receive).  Returns the number of pieces. */
+int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
 
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).

@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split",
 ]
 
 
@@ -156,6 +156,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_comm_init_local.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sylver_b200_partition.argtypes = [vp, C.c_int, vp]
     L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.sylver_b200_plan_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -250,6 +251,19 @@ def partition(solver: "Solver", world: int) -> np.ndarray:
     own = np.zeros(max(nn, 1), dtype=np.int32)
     lib().sylver_b200_partition(solver.akeep, world, _ptr(own))
     return own[:nn]
+
+
+def plan_split(solver: "Solver", rank: int, world: int):
+    """Host-only positive definite plan of `rank` among `world` ranks (sylver_b200_plan_split):
+    (summary dict, pieces array of rows (level, front, peer, offset, count, direction))."""
+    out = np.zeros(8, dtype=np.int64)
+    cnt = lib().sylver_b200_plan_split(solver.akeep, rank, world, _ptr(out), 0, None)
+    if cnt < 0:
+        raise RuntimeError("sylver_b200_plan_split failed")
+    pieces = np.zeros((max(cnt, 1), 6), dtype=np.int64)
+    lib().sylver_b200_plan_split(solver.akeep, rank, world, _ptr(out), 6 * cnt, _ptr(pieces))
+    keys = ("split_fronts", "split_member", "factor_bytes", "contrib_bytes", "stage_bytes", "sends", "recvs", "max_ops_level")
+    return dict(zip(keys, (int(v) for v in out))), pieces[:cnt]
 
 
 def plan_exchanges(solver: "Solver", rank: int, world: int) -> np.ndarray:

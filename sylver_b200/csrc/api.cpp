@@ -448,6 +448,12 @@ int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* o
    return cnt;
 }
 
+int sylver_b200_plan_split(void* akeep, int rank, int world, long* out8, int cap, long* pieces) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   if (!ak || !ak->analysed || !ak->tree || world < 1 || rank < 0 || rank >= world) return -1;
+   return numeric_plan_split(ak->tree, rank, world, out8, cap, pieces);
+}
+
 int sylver_b200_numeric_tree_get_front_indef(void const* tree, int node, int* nelim, double* d, int* perm) {
    if (!tree) return -1;
    return numeric_tree_get_front_indef(static_cast<const NumericTree*>(tree), node, nelim, d, perm);

@@ -423,7 +423,7 @@ void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int r
 }
 
 // owned fronts per level (order of st->level_nodes preserved: ncol descending)
-void plan_owned_levels(NumericTree* nt) {
+void plan_owned_levels(NumericTree* nt, bool upload) {
    SymbolicTree* st = nt->st;
    nt->lvl_ptr.assign(st->nlevels + 1, 0);
    nt->lvl_nodes.clear();
@@ -432,6 +432,7 @@ void plan_owned_levels(NumericTree* nt) {
          if (nt->owner[st->level_nodes[i]] == nt->rank) nt->lvl_nodes.push_back(st->level_nodes[i]);
       nt->lvl_ptr[l + 1] = (int)nt->lvl_nodes.size();
    }
+   if (!upload) return;
    if (nt->d_lvl_nodes) cudaFree(nt->d_lvl_nodes);
    nt->d_lvl_nodes = dev_upload(nt->lvl_nodes);
 }
@@ -442,7 +443,7 @@ void plan_owned_levels(NumericTree* nt) {
 // by the members of its group.  Every rank that works on the parent needs every piece.  All
 // ranks enumerate (level, front, piece, destination) in the same order, so the sends and
 // receives of a rank pair match up.
-static void plan_split(NumericTree* nt) {
+static void plan_split(NumericTree* nt, bool device) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes, me = nt->rank, nb = nt->nb;
    nt->fac_ptr.assign(st->nlevels + 1, 0);
@@ -495,6 +496,9 @@ static void plan_split(NumericTree* nt) {
       }
       nt->fac_ptr[l + 1] = (int)nt->fac_nodes.size();
    }
+   nt->stage_doubles = stage;
+   nt->split_fronts = split_fronts;
+   if (!device) return;      // host-only planning (sylver_b200_plan_split, CPU tests)
    // sub-communicators: every rank of the world walks the same (deterministic) list of groups
    if (nt->world > 1) {
       std::vector<std::pair<int, int>> groups;
@@ -532,10 +536,12 @@ static void plan_split(NumericTree* nt) {
    }
 }
 
-static void build_posdef_plan(NumericTree* nt) {
+// Host-only part of the positive definite plan (no CUDA, no communicator): who works on which
+// front, split fronts, arena offsets, exchange lists.  `device` adds the uploads and the
+// sub-communicators.
+void posdef_plan_host(NumericTree* nt, bool device) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
-   const int nb = nt->nb;
    nt->m.resize(N); nt->n.resize(N); nt->ldl.resize(N);
    nt->loff.resize(N);
    const int me = nt->rank;
@@ -568,8 +574,16 @@ static void build_posdef_plan(NumericTree* nt) {
    nt->L_doubles = loff + 4;
    plan_contrib_arena(nt);
    plan_exchanges(*st, nt->owner, me, nt->sends, nt->recvs);
-   plan_owned_levels(nt);
-   plan_split(nt);
+   plan_owned_levels(nt, device);
+   plan_split(nt, device);
+}
+
+static void build_posdef_plan(NumericTree* nt) {
+   SymbolicTree* st = nt->st;
+   const int N = st->nnodes;
+   const int nb = nt->nb;
+   const int me = nt->rank;
+   posdef_plan_host(nt, true);
 
    // work lists
    std::vector<int> prefix;
@@ -1231,6 +1245,44 @@ void numeric_tree_timings(const NumericTree* nt, double* out4) {
    out4[1] = nt->t_h2d;
    out4[2] = nt->t_wall;
    out4[3] = (double)nt->launches;
+}
+
+// Host-only: the positive definite plan of `rank` in a world of `world` ranks (no CUDA, no
+// communicator).  out8: split fronts in the tree, split fronts this rank works on, factor arena
+// bytes, contribution arena bytes, panel staging bytes, pieces sent, pieces received, largest
+// number of point-to-point operations in one level.  pieces (6 longs each, at most cap/6):
+// level, front (topmost reference node), peer, offset, count (doubles), direction (0 send, 1 recv).
+int numeric_plan_split(SymbolicTree* st, int rank, int world, long* out8, int cap, long* pieces) {
+   NumericTree nt;
+   nt.st = st;
+   nt.rank = rank;
+   nt.world = world;
+   nt.nb = 128;
+   posdef_plan_host(&nt, false);
+   for (int i = 0; i < 8; ++i) out8[i] = 0;
+   for (int f = 0; f < st->nnodes; ++f)
+      if (nt.splitP[f] > 1) {
+         ++out8[0];
+         if (in_dest(&nt, f, rank)) ++out8[1];
+      }
+   out8[2] = (long)(nt.L_doubles * sizeof(double));
+   out8[3] = (long)(nt.C_doubles * sizeof(double));
+   out8[4] = (long)(nt.stage_doubles * sizeof(double));
+   int cnt = 0;
+   for (int l = 0; l < st->nlevels; ++l) {
+      out8[5] += (long)nt.csends[l].size();
+      out8[6] += (long)nt.crecvs[l].size();
+      out8[7] = std::max<long>(out8[7], (long)(nt.csends[l].size() + nt.crecvs[l].size()));
+      for (int dir = 0; dir < 2; ++dir)
+         for (const Piece& x : (dir == 0 ? nt.csends[l] : nt.crecvs[l])) {
+            if (6 * cnt + 5 < cap) {
+               long* o = pieces + 6 * cnt;
+               o[0] = l; o[1] = st->ref_top[x.f]; o[2] = x.peer; o[3] = x.off; o[4] = (long)x.count; o[5] = dir;
+            }
+            ++cnt;
+         }
+   }
+   return cnt;
 }
 
 void numeric_tree_split_info(const NumericTree* nt, int* out3) {

@@ -197,6 +197,7 @@ struct NumericTree {
    int* d_fac_nodes = nullptr;
    std::vector<std::vector<SplitPlan>> splits;    // per level: split fronts this rank is a member of
    std::vector<std::vector<Piece>> csends, crecvs;   // per level: contribution pieces crossing GPUs
+   std::vector<int> split_fronts;                 // fronts of `splits`, in slot order
    int* d_split_fronts = nullptr;
    int* d_zero = nullptr;
    double* d_stage = nullptr; size_t stage_doubles = 0;
@@ -253,7 +254,8 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats);
 void indef_setup(NumericTree* nt);
 void indef_destroy(NumericTree* nt);
 void plan_contrib_arena(NumericTree* nt);
-void plan_owned_levels(NumericTree* nt);
+void plan_owned_levels(NumericTree* nt, bool upload = true);
+void posdef_plan_host(NumericTree* nt, bool device);
 void upload_geometry(NumericTree* nt);
 void load_values(NumericTree* nt, const double* aval, const double* scaling);
 

@@ -1,0 +1,127 @@
+"""Host-side logic added for the top of the tree (no GPU needed): the engine-internal chain
+coarsening of the assembly tree and the multi-GPU plan with fronts split over rank groups
+(SURVEY.md 8e).  The numerical side of both is covered by tests/test_gpu_local_ranks.py."""
+import os
+
+import numpy as np
+import pytest
+
+import sylver_b200 as sb
+from sylver_b200 import gen
+
+
+def analysed(kind, k, monkeypatch=None, amalgamate=None):
+    if amalgamate is not None:
+        monkeypatch.setenv("SYLVER_B200_AMALGAMATE", amalgamate)
+    if kind == "kkt":
+        n, ptr, row, val = gen.stokes_kkt(k)
+        order = gen.nested_dissection_order(k, dofs_per_cell=4)
+    else:
+        n, ptr, row, val = (gen.laplacian_7pt if kind == "lap7" else gen.laplacian_27pt)(k)
+        order = gen.nested_dissection_order(k)
+    s = sb.Solver()
+    assert s.analyse(n, ptr, row, order).flag == 0
+    return s, n
+
+
+@pytest.mark.parametrize("kind,k", [("lap7", 16), ("lap7", 24), ("lap27", 12), ("kkt", 8)])
+def test_chain_coarsening_invariants(lib, monkeypatch, kind, k):
+    s, n = analysed(kind, k)
+    sym, et = s.symbolic(), s.engine_tree()
+    nref, G = sym["nnodes"], et["nnodes"]
+    nmap = et["node_map"]
+    ncol = np.diff(sym["sptr"]).astype(np.int64)
+    nrow = np.diff(sym["rptr"]).astype(np.int64)
+    par = sym["sparent"] - 1
+    assert len(nmap) == nref and G <= nref
+    # groups are runs of consecutive reference nodes, numbered in order
+    assert nmap[0] == 0 and nmap[-1] == G - 1
+    assert ((np.diff(nmap) == 0) | (np.diff(nmap) == 1)).all()
+    assert int(et["ncol"].sum()) == n
+    zeros_total = 0
+    for g in range(G):
+        members = np.nonzero(nmap == g)[0]
+        a, b = members[0], members[-1]
+        # a chain: every member but the top is the LAST child (= the node right before) of the next
+        for i in range(a, b):
+            assert par[i] == i + 1
+        assert et["ncol"][g] == ncol[a:b + 1].sum()
+        assert et["nrow"][g] == ncol[a:b + 1].sum() + (nrow[b] - ncol[b])
+        # the engine parent is the group of the top member's reference parent
+        assert et["parent"][g] == (nmap[par[b]] if par[b] < nref else G)
+        # explicit zeros added to member j's columns: rows of the merged front it did not have
+        for j in range(a, b + 1):
+            rows_in_merged = et["nrow"][g] - (ncol[a:j].sum())
+            zeros_total += int(ncol[j] * (rows_in_merged - nrow[j]))
+            assert rows_in_merged >= nrow[j]
+    panel = int((et["nrow"].astype(np.int64) * et["ncol"]).sum())
+    assert zeros_total <= 0.05 * panel
+    if kind == "lap7":
+        assert G < nref                      # the separator chains of the 7-point stencil collapse
+    # the reference-structure outputs are untouched by the coarsening
+    cptr, cmap = s.cmap()
+    s.free()
+    s0, _ = analysed(kind, k, monkeypatch, "0")
+    et0 = s0.engine_tree()
+    assert et0["nnodes"] == nref and np.array_equal(et0["node_map"], np.arange(nref))
+    cptr0, cmap0 = s0.cmap()
+    assert np.array_equal(cptr, cptr0) and np.array_equal(cmap, cmap0)
+    s0.free()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("kind,k", [("lap27", 16), ("lap7", 24)])
+def test_split_plan_pairs_up_and_covers(lib, monkeypatch, kind, k, world):
+    """Every piece a rank sends is received by its peer at the same level with the same extent,
+    in the same order per ordered rank pair (what NCCL's grouped send/recv matching needs), every
+    rank that works on a parent front ends up with every piece of each child's block exactly
+    once, and the pieces of a block do not overlap."""
+    monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "48")
+    s, n = analysed(kind, k)
+    sym = s.symbolic()
+    plans = [sb.plan_split(s, r, world) for r in range(world)]
+    assert plans[0][0]["split_fronts"] >= 1
+    assert sum(p[0]["split_member"] for p in plans) >= 2 * plans[0][0]["split_fronts"]
+    sends = {}
+    recvs = {}
+    for r, (_, pieces) in enumerate(plans):
+        for (l, f, peer, off, count, d) in pieces.tolist():
+            assert peer != r and count > 0 and off >= 0
+            (sends if d == 0 else recvs).setdefault((r, peer) if d == 0 else (peer, r), []).append((l, f, off, count))
+    assert sends.keys() == recvs.keys() and len(sends) > 0
+    for pair in sends:
+        assert sends[pair] == recvs[pair], pair          # same order on both sides
+    # coverage: per (front, destination rank) the received pieces are disjoint intervals
+    got = {}
+    for (src, dst), lst in recvs.items():
+        for (l, f, off, count) in lst:
+            got.setdefault((f, dst), []).append((off, off + count, src))
+    for (f, dst), iv in got.items():
+        iv.sort()
+        for (a0, a1, _), (b0, b1, _) in zip(iv, iv[1:]):
+            assert a1 <= b0, (f, dst)
+    # an unsplit front's block travels as one piece of k * ldc doubles from its owner
+    own = sb.partition(s, world)
+    k_ref = (np.diff(sym["rptr"]) - np.diff(sym["sptr"])).astype(np.int64)
+    for (f, dst), iv in got.items():
+        if len(iv) == 1 and iv[0][0] == 0:
+            ldc = (max(int(k_ref[f]), 1) + 3) // 4 * 4
+            if iv[0][1] == k_ref[f] * ldc:
+                assert iv[0][2] == own[f]
+    # memory: split fronts are replicated over their group, nothing else is
+    single = sb.plan_split(s, 0, 1)[0]
+    assert single["split_fronts"] == 0 and single["sends"] == 0
+    assert sum(p[0]["factor_bytes"] for p in plans) >= single["factor_bytes"]
+    assert max(p[0]["factor_bytes"] for p in plans) < single["factor_bytes"]
+    s.free()
+
+
+def test_split_can_be_disabled(lib, monkeypatch):
+    monkeypatch.setenv("SYLVER_B200_SPLIT", "0")
+    s, _ = analysed("lap27", 12)
+    for r in range(4):
+        d, pieces = sb.plan_split(s, r, 4)
+        assert d["split_fronts"] == 0
+        # without split fronts every cross-rank edge is one whole-block piece
+        assert all(off == 0 for (_, _, _, off, _, _) in pieces.tolist())
+    s.free()
