@@ -67,7 +67,9 @@ typedef struct {
    int nemin;                 /* 32 */
    bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
    long min_gpu_work;
-   int scaling;               /* <=0: none / user supplied */
+   int scaling;               /* <=0: none / user supplied in `scale`; >=4: norm equilibration
+                                 computed at factorize (MC77-like); 1..3 (MC64, auction, saved
+                                 matching scaling): flag -98 */
    int pivot_method;          /* 1 APP aggressive, 2 APP block, 3 TPP */
    double small;              /* 1e-20 */
    double u;                  /* 0.01 */
@@ -119,7 +121,9 @@ void sylver_default_options(sylver_options_t *options);
 void spldlt_analyse(int n, int *order, long const *ptr, int const *row,
                     double const *val, void **akeep, bool check,
                     sylver_options_t const *options, sylver_inform_t *inform);
-/* sylver.h:95-98 */
+/* sylver.h:95-98.  val: host or device pointer.  scale (n doubles, original order, may be
+ * NULL): read when options->scaling <= 0 (user scaling), written when options->scaling >= 4
+ * (the equilibration scaling computed here, spldlt_factorize_mod.F90:804-831; needs ptr/row). */
 void spldlt_factorize(bool posdef, long const *ptr, int const *row,
                       double const *val, double *scale, void *akeep, void **fkeep,
                       sylver_options_t const *options, sylver_inform_t *inform);
@@ -307,6 +311,12 @@ int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *o
  * offset and count (doubles, inside the front's contribution block), direction (0 send, 1
  * receive).  Returns the number of pieces. */
 int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
+
+/* The scaling spldlt_factorize computes for options->scaling >= 4, on its own (host only):
+ * symmetric infinity-norm equilibration of the lower-triangle CSC matrix (1-based ptr/row),
+ * SPRAL inf_norm_equilib_sym (spral/src/scaling.f90:480-521).  scaling: n doubles out.
+ * Returns the number of iterations the reference would report, or -1 on bad arguments. */
+int sylver_b200_equilib_scale(int n, long const *ptr, int const *row, double const *val, double *scaling);
 
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).

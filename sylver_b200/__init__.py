@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale",
 ]
 
 
@@ -157,6 +157,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_partition.argtypes = [vp, C.c_int, vp]
     L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.sylver_b200_plan_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.sylver_b200_equilib_scale.argtypes = [C.c_int, vp, vp, vp, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -251,6 +252,19 @@ def partition(solver: "Solver", world: int) -> np.ndarray:
     own = np.zeros(max(nn, 1), dtype=np.int32)
     lib().sylver_b200_partition(solver.akeep, world, _ptr(own))
     return own[:nn]
+
+
+def equilib_scale(n: int, ptr, row, val):
+    """Norm-equilibration scaling of a lower-triangle CSC matrix (sylver_b200_equilib_scale):
+    (scaling, iterations)."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    row = np.ascontiguousarray(row, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    sc = np.zeros(max(n, 1))
+    it = lib().sylver_b200_equilib_scale(n, _ptr(ptr), _ptr(row), _ptr(val), _ptr(sc))
+    if it < 0:
+        raise RuntimeError("sylver_b200_equilib_scale failed")
+    return sc[:n], it
 
 
 def plan_split(solver: "Solver", rank: int, world: int):

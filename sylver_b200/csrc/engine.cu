@@ -1164,6 +1164,10 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       // values: the map references entries 1..max(src)
       nt->aval_count = (size_t)st->nval;
       CU_TRY(cudaMalloc(&nt->d_aval, std::max<size_t>(nt->aval_count, 1) * sizeof(double)));
+      // the scaling buffer must exist before the launch sequence is captured: its address is a
+      // kernel argument inside the CUDA graph (a tree is created with or without scaling and
+      // keeps that property; api.cpp builds a new tree when it changes)
+      if (scaling) CU_TRY(cudaMalloc(&nt->d_scaling, std::max(st->n, 1) * sizeof(double)));
       if (!posdef) {
          indef_setup(nt);
          load_values(nt, aval, scaling);
@@ -1283,6 +1287,21 @@ int numeric_plan_split(SymbolicTree* st, int rank, int world, long* out8, int ca
          }
    }
    return cnt;
+}
+
+// Values as host memory: `val` itself, or a copy in `tmp` when it is a device pointer.
+const double* values_on_host(const double* val, size_t count, std::vector<double>& tmp) {
+   cudaPointerAttributes attr{};
+   bool on_dev = false;
+   if (cudaPointerGetAttributes(&attr, val) == cudaSuccess) on_dev = attr.type == cudaMemoryTypeDevice;
+   else cudaGetLastError();
+   if (!on_dev) return val;
+   tmp.resize(count);
+   if (cudaMemcpy(tmp.data(), val, count * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+   }
+   return tmp.data();
 }
 
 void numeric_tree_split_info(const NumericTree* nt, int* out3) {

@@ -103,6 +103,8 @@ int numeric_tree_get_front(const NumericTree* nt, int node, int* m, int* n, doub
 int numeric_tree_get_front_indef(const NumericTree* nt, int node, int* nelim, double* d, int* perm);
 
 int device_count();
+// `val` if it is host memory, else a host copy in tmp (nullptr if the copy fails)
+const double* values_on_host(const double* val, size_t count, std::vector<double>& tmp);
 int numeric_tree_profile(const NumericTree* nt, double* out, int cap);
 void set_user_stream(void* stream, bool enable);
 long numeric_tree_bytes(const NumericTree* nt, long* factor_bytes, long* contrib_bytes);
