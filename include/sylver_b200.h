@@ -277,8 +277,12 @@ int sylver_b200_numeric_tree_get_front_indef(void const *tree, int node, int *ne
  * Here every rank runs the same analyse; spldlt_factorize then factorizes the fronts the
  * deterministic partition (sylver_b200_partition) gives to this rank and moves the
  * contribution blocks of cross-GPU tree edges with ncclSend/ncclRecv.  spldlt_solve works on a
- * replicated right-hand side and returns the full solution on every rank.  (Positive
- * definite factorizations only in this version; posdef=false with world>1 -> flag -98.)
+ * replicated right-hand side and returns the full solution on every rank.  Positive definite
+ * factorizations additionally split the widest fronts above the partition cut over their rank
+ * group (block-column cyclic, panels by ncclBroadcast on ncclCommSplit sub-communicators;
+ * environment SYLVER_B200_SPLIT=0 disables, SYLVER_B200_SPLIT_MIN = minimum columns, default
+ * 1024).  Indefinite (APTP) factorizations exchange the eliminated counts, contribution blocks
+ * and delayed columns per level; their fronts are not split.
  *   rank 0:    sylver_b200_comm_unique_id(id)   (128 bytes; broadcast it by any means)
  *   all ranks: cudaSetDevice(local gpu); sylver_b200_comm_init(rank, world, id)       */
 int sylver_b200_comm_unique_id(void *out128);
