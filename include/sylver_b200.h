@@ -67,9 +67,9 @@ typedef struct {
    int nemin;                 /* 32 */
    bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
    long min_gpu_work;
-   int scaling;               /* <=0: none / user supplied in `scale`; >=4: norm equilibration
-                                 computed at factorize (MC77-like); 1..3 (MC64, auction, saved
-                                 matching scaling): flag -98 */
+   int scaling;               /* <=0: none / user supplied in `scale`; 2: auction matching;
+                                 >=4: norm equilibration (MC77-like), both computed at factorize;
+                                 1 (MC64) and 3 (saved matching scaling): flag -98 */
    int pivot_method;          /* 1 APP aggressive, 2 APP block, 3 TPP */
    double small;              /* 1e-20 */
    double u;                  /* 0.01 */
@@ -122,8 +122,8 @@ void spldlt_analyse(int n, int *order, long const *ptr, int const *row,
                     double const *val, void **akeep, bool check,
                     sylver_options_t const *options, sylver_inform_t *inform);
 /* sylver.h:95-98.  val: host or device pointer.  scale (n doubles, original order, may be
- * NULL): read when options->scaling <= 0 (user scaling), written when options->scaling >= 4
- * (the equilibration scaling computed here, spldlt_factorize_mod.F90:804-831; needs ptr/row). */
+ * NULL): read when options->scaling <= 0 (user scaling), written when options->scaling is 2 or
+ * >= 4 (the scaling computed here, spldlt_factorize_mod.F90:771-795,804-831; needs ptr/row). */
 void spldlt_factorize(bool posdef, long const *ptr, int const *row,
                       double const *val, double *scale, void *akeep, void **fkeep,
                       sylver_options_t const *options, sylver_inform_t *inform);
@@ -321,6 +321,12 @@ int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap
  * SPRAL inf_norm_equilib_sym (spral/src/scaling.f90:480-521).  scaling: n doubles out.
  * Returns the number of iterations the reference would report, or -1 on bad arguments. */
 int sylver_b200_equilib_scale(int n, long const *ptr, int const *row, double const *val, double *scaling);
+/* The scaling of options->scaling == 2: matching-based scaling by the auction algorithm with
+ * SPRAL's default auction_options (auction_scale_sym, spral/src/scaling.f90:269-309,1351-1719).
+ * match (n ints, may be NULL): match[i] = 1-based column matched to row i+1, 0 = unmatched.
+ * inform4 (may be NULL) = { flag, matched, iterations, unmatchable }.  Returns 0, or -1. */
+int sylver_b200_auction_scale(int n, long const *ptr, int const *row, double const *val, double *scaling,
+                              int *match, int *inform4);
 
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).

@@ -14,6 +14,7 @@
 #include "analyse.hpp"
 #include "comm.hpp"
 #include "engine.hpp"
+#include "scaling.hpp"
 
 using namespace sylver_b200;
 
@@ -39,36 +40,6 @@ struct FKeep {
 };
 
 int g_ngpu = 1;
-
-// Symmetric infinity-norm equilibration (options.scaling >= 4): restatement of SPRAL's
-// inf_norm_equilib_sym (spral/src/scaling.f90:480-521; Knight, Ruiz, Ucar: "A symmetry preserving
-// algorithm for matrix scaling", Algorithm 1) with equilib_options' defaults max_iterations = 10,
-// tol = 1e-8 (a default REAL, scaling.f90:29-32).  Lower triangle, 1-based ptr/row.  Returns the
-// iteration count the reference reports (itr - 1).
-int equilib_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling) {
-   const int max_iterations = 10;
-   const double tol = (double)1e-8f;
-   std::vector<double> maxentry(n);
-   for (int i = 0; i < n; ++i) scaling[i] = 1.0;
-   int itr = 1;
-   for (; itr <= max_iterations; ++itr) {
-      std::fill(maxentry.begin(), maxentry.end(), 0.0);
-      for (int c = 0; c < n; ++c)
-         for (long j = ptr[c] - 1; j < ptr[c + 1] - 1; ++j) {
-            const int r = row[j] - 1;
-            const double v = std::fabs(scaling[r] * val[j] * scaling[c]);
-            maxentry[r] = std::max(maxentry[r], v);
-            maxentry[c] = std::max(maxentry[c], v);
-         }
-      double dev = 0.0;
-      for (int i = 0; i < n; ++i) {
-         if (maxentry[i] > 0) scaling[i] = scaling[i] / std::sqrt(maxentry[i]);
-         dev = std::max(dev, std::fabs(1 - maxentry[i]));
-      }
-      if (dev < tol) break;
-   }
-   return itr - 1;      // Fortran: the loop variable is max_iterations + 1 when the loop runs out
-}
 
 sylver_inform_t inform_default() {
    sylver_inform_t inf;
@@ -217,26 +188,35 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
    if (!options->action && n != ak->inform.matrix_rank) { inform->flag = SYLVER_ERROR_SINGULAR; fk->inform = *inform; return; }
    if (ak->sym.nnodes == 0) { inform->flag = SYLVER_SUCCESS; inform->matrix_rank = 0; fk->inform = *inform; return; }
    if (!val) { inform->flag = SYLVER_ERROR_VAL; fk->inform = *inform; return; }
-   if (options->scaling > 0 && options->scaling < 4) {
-      // MC64 (1), auction (2) and matching-order (3) scalings are pre-processing outside this
-      // path; a scaling computed elsewhere can be passed in `scale`
+   if (options->scaling == 1 || options->scaling == 3) {
+      // MC64 (1) and the matching-order scaling saved by analyse (3) are pre-processing outside
+      // this path; a scaling computed elsewhere can be passed in `scale`
       inform->flag = SYLVER_ERROR_UNIMPLEMENTED;
       fk->inform = *inform;
       return;
    }
    const bool had_scaling = !fk->scaling.empty();
    fk->scaling.clear();
-   if (options->scaling >= 4) {
-      // norm equilibration computed here (spldlt_factorize_mod.F90:804-831)
+   if (options->scaling == 2 || options->scaling >= 4) {
+      // computed here: auction matching (2, spldlt_factorize_mod.F90:771-795) or norm
+      // equilibration (>= 4, :804-831); permuted to elimination order, handed back in `scale`
       if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; fk->inform = *inform; return; }
       std::vector<double> tmp, scaling(n);
       const double* hval = values_on_host(val, (size_t)(ptr[n] - 1), tmp);
       if (!hval) { inform->flag = SYLVER_ERROR_CUDA_UNKNOWN; fk->inform = *inform; return; }
-      equilib_scale_sym(n, ptr, row, hval, scaling.data());
+      if (options->scaling == 2) {
+         if (auction_scale_sym(n, ptr, row, hval, scaling.data(), nullptr, nullptr) != 0) {
+            inform->flag = SYLVER_ERROR_ALLOCATION;
+            fk->inform = *inform;
+            return;
+         }
+      } else {
+         equilib_scale_sym(n, ptr, row, hval, scaling.data());
+      }
       fk->scaling.resize(n);
       for (int i = 0; i < n; ++i) fk->scaling[i] = scaling[ak->sym.invp[i] - 1];
       if (scale)
-         for (int i = 0; i < n; ++i) scale[ak->sym.invp[i] - 1] = fk->scaling[i];
+         for (int i = 0; i < n; ++i) scale[i] = scaling[i];
    } else if (scale) {
       // user supplied scaling, permuted to elimination order (spldlt_factorize_mod.F90:744-749)
       fk->scaling.resize(n);
@@ -496,6 +476,15 @@ int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* o
 int sylver_b200_equilib_scale(int n, long const* ptr, int const* row, double const* val, double* scaling) {
    if (n < 0 || !ptr || !row || !val || !scaling) return -1;
    return equilib_scale_sym(n, ptr, row, val, scaling);
+}
+
+int sylver_b200_auction_scale(int n, long const* ptr, int const* row, double const* val, double* scaling,
+                              int* match, int* inform4) {
+   if (n < 0 || !ptr || !row || !val || !scaling) return -1;
+   AuctionInform inf;
+   const int flag = auction_scale_sym(n, ptr, row, val, scaling, match, &inf);
+   if (inform4) { inform4[0] = inf.flag; inform4[1] = inf.matched; inform4[2] = inf.iterations; inform4[3] = inf.unmatchable; }
+   return flag;
 }
 
 int sylver_b200_plan_split(void* akeep, int rank, int world, long* out8, int cap, long* pieces) {

@@ -1,0 +1,26 @@
+// Matrix scalings computed at factorize (host code): restatements of SPRAL's scaling module
+// (spral/src/scaling.f90), which the reference calls from spldlt_factorize
+// (src/spldlt_factorize_mod.F90:727-835).
+#pragma once
+
+namespace sylver_b200 {
+
+// options%scaling >= 4: symmetric infinity-norm equilibration (scaling.f90:480-521).
+// Returns the iteration count the reference reports.
+int equilib_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling);
+
+// options%scaling == 2: matching-based scaling by the auction algorithm
+// (auction_scale_sym, scaling.f90:269-309 -> auction_match :1504-1609 -> auction_match_core
+// :1351-1489 -> match_postproc :1611-1719), default auction_options (:33-38).
+struct AuctionInform {
+   int flag = 0;
+   int matched = 0;
+   int iterations = 0;
+   int unmatchable = 0;
+};
+// Lower triangle CSC, 1-based ptr/row.  match (n ints, may be null): match[i] = column (1-based)
+// matched to row i, 0 = unmatched.  Returns inform.flag (0, or -1 on allocation failure).
+int auction_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling, int* match,
+                      AuctionInform* inform);
+
+}  // namespace sylver_b200

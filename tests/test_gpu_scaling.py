@@ -1,5 +1,5 @@
 """Scaled factorizations on the GPU: options.scaling >= 4 (norm
-equilibration computed at factorize) and a user-supplied scaling.  The matrices are Laplacian /
+equilibration) and == 2 (auction matching), both computed at factorize, and a user-supplied scaling.  The matrices are Laplacian /
 KKT systems with rows and columns scaled by 10^U(-4,4): the scaled backward error of the solve
 must be <= 1e-14 and within 10x of the SSIDS CPU oracle run with the same scaling vector."""
 import numpy as np
@@ -17,20 +17,21 @@ def _order(kind, k):
     return gen.nested_dissection_order(k, dofs_per_cell=4) if kind == "kkt" else gen.nested_dissection_order(k)
 
 
+@pytest.mark.parametrize("mode", [4, 2], ids=["equilib", "auction"])
 @pytest.mark.parametrize("kind,k,posdef", [("lap27", 10, True), ("lap7", 14, True), ("lap7", 14, False), ("kkt", 8, False)])
-def test_equilibrated_factorization(lib, oracle_ref, kind, k, posdef):
+def test_scaled_factorization(lib, oracle_ref, kind, k, posdef, mode):
     sb.require_gpu()
     n, ptr, row, val = badly_scaled(kind, k, 7)
     order = _order(kind, k)
     b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
     s = sb.Solver()
     assert s.analyse(n, ptr, row, order).flag == 0
-    s.options.scaling = 4
+    s.options.scaling = mode
     scale = np.zeros(n)
     inf = s.factorize(val, posdef=posdef, scale=scale)
     assert inf.flag >= 0, inf.flag
     # the scaling handed back is the one the host routine computes (original order)
-    sc, _ = sb.equilib_scale(n, ptr, row, val)
+    sc = sb.equilib_scale(n, ptr, row, val)[0] if mode == 4 else sb.auction_scale(n, ptr, row, val)[0]
     assert np.array_equal(scale, sc)
     x = s.solve(b)
     be = gen.backward_error(n, ptr, row, val, x, b)

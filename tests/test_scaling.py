@@ -1,6 +1,8 @@
-"""options.scaling >= 4 (norm equilibration): the product's C++ against the
-numpy restatement of SPRAL's inf_norm_equilib_sym (oracle/scaling.py), bit for bit, and against
-the property the iteration converges to.  No GPU needed."""
+"""Scalings computed at factorize, host code, no GPU needed:
+options.scaling >= 4 (norm equilibration) and == 2 (auction matching).  The product's C++
+(csrc/scaling.cpp) is compared bit for bit with the restatements of SPRAL's Fortran in
+oracle/scaling.py, and both are held to the properties the reference's own tests check
+(spral/tests/scaling.f90: test_auction_sym_random :46-184, test_equilib_sym_random :400-457)."""
 import numpy as np
 import pytest
 
@@ -60,12 +62,114 @@ def test_equilib_edge_cases(lib):
 
 
 def test_scaling_options_are_rejected_or_accepted(lib):
-    """1..3 (MC64, auction, saved matching scaling) stay outside this path: flag -98 without a
-    GPU being touched; >= 4 needs the structure arrays."""
+    """1 and 3 (MC64, saved matching scaling) stay outside this path: flag -98 without a GPU
+    being touched."""
     n, ptr, row, val = gen.laplacian_7pt(4)
     s = sb.Solver()
     assert s.analyse(n, ptr, row, gen.nested_dissection_order(4)).flag == 0
-    for sc in (1, 2, 3):
+    for sc in (1, 3):
         s.options.scaling = sc
         assert s.factorize(val, posdef=True).flag == -98
     s.free()
+
+
+def random_sym(n, nza, rng, wide=False):
+    """Random sparse symmetric matrix, lower triangle CSC 1-based, every column non-empty, about
+    nza entries: uniform in (-1, 1) like the reference test's gen_random_sym
+    (spral/src/random_matrix.f90), or with magnitudes over twelve orders (wide)."""
+    cols = []
+    ptr = [1]
+    rows_all, vals_all = [], []
+    extra = max(nza - n, 0)
+    per_col = rng.multinomial(extra, np.ones(n) / n) if n else []
+    for j in range(n):
+        cand = np.arange(j + 1, n)
+        k = min(int(per_col[j]), len(cand))
+        r = np.sort(rng.choice(cand, size=k, replace=False)) if k else np.zeros(0, dtype=np.int64)
+        r = np.concatenate([[j], r])
+        rows_all.append(r + 1)
+        if wide:
+            vals_all.append(rng.choice([-1.0, 1.0], len(r)) * 10.0 ** rng.uniform(-6, 6, len(r)))
+        else:
+            v = rng.uniform(-1.0, 1.0, len(r))
+            vals_all.append(np.where(v == 0.0, 0.5, v))
+        ptr.append(ptr[-1] + len(r))
+    return (np.array(ptr, dtype=np.int64), np.concatenate(rows_all).astype(np.int32) if n else np.zeros(0, np.int32),
+            np.concatenate(vals_all) if n else np.zeros(0))
+
+
+def check_auction_properties(n, ptr, row, val, scaling, match, scaled_entries=True):
+    # spral/tests/scaling.f90:113-152: matching is valid, injective, covers >= 90 %
+    assert ((match >= 0) & (match <= n)).all()
+    ent = set()
+    for j in range(n):
+        for k in range(ptr[j] - 1, ptr[j + 1] - 1):
+            ent.add((int(row[k]), j + 1))
+            ent.add((j + 1, int(row[k])))
+    nz = match[match != 0]
+    assert len(np.unique(nz)) == len(nz)
+    for i in range(n):
+        if match[i]:
+            assert (i + 1, int(match[i])) in ent
+    assert len(nz) >= 0.9 * n
+    if not scaled_entries:
+        return
+    # :157-179: every scaled entry < 2, every row has one >= 0.75
+    mx = row_inf_norms(n, ptr, row, val, scaling)
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    assert (np.abs(scaling[row - 1] * val * scaling[col]) < 2.0).all()
+    assert (mx >= 0.75).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_auction_matches_restatement_and_reference_properties(lib, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = seed + 1 if seed < 5 else int(rng.integers(20, 160))         # very small problems first, as the reference
+    nza = n + int(rng.integers(0, max(n * n // 2 - n, 0) + 1)) // (1 if n < 30 else 8)
+    ptr, row, val = random_sym(n, nza, rng)
+    s, m, inf = sb.auction_scale(n, ptr, row, val)
+    so, mo, info = oscal.auction_scale_sym(n, ptr, row, val)
+    assert inf == info
+    assert np.array_equal(m, mo)
+    assert np.array_equal(s, so)
+    check_auction_properties(n, ptr, row, val, s, m)
+    # entries spread over twelve orders of magnitude: same code path, bitwise agreement; the
+    # early termination (90 % matched) leaves a few rows further from 1 than the reference's
+    # test family, so only the matching is checked
+    ptr, row, val = random_sym(n, nza, rng, wide=True)
+    s, m, inf = sb.auction_scale(n, ptr, row, val)
+    so, mo, info = oscal.auction_scale_sym(n, ptr, row, val)
+    assert inf == info and np.array_equal(m, mo) and np.array_equal(s, so)
+    assert len(np.unique(m[m != 0])) == int((m != 0).sum())
+
+
+@pytest.mark.parametrize("kind,k,seed", [("lap7", 7, 1), ("lap27", 5, 2), ("kkt", 5, 3)])
+def test_auction_on_the_benchmark_families(lib, kind, k, seed):
+    n, ptr, row, val = badly_scaled(kind, k, seed)
+    s, m, inf = sb.auction_scale(n, ptr, row, val)
+    so, mo, info = oscal.auction_scale_sym(n, ptr, row, val)
+    assert inf == info and np.array_equal(m, mo) and np.array_equal(s, so)
+    # rows and columns scaled by 10^U(-4,4): the few rows the early termination leaves
+    # unmatched end further from 1 than on the reference's test family
+    check_auction_properties(n, ptr, row, val, s, m, scaled_entries=False)
+    mx = row_inf_norms(n, ptr, row, val, s)
+    assert np.median(mx) > 0.9 and mx.max() < 2.0
+    # an explicit zero is dropped before the matching (scaling.f90:1546), not treated as an entry
+    val0 = val.copy()
+    off = int(np.nonzero(row != np.repeat(np.arange(n), np.diff(ptr)) + 1)[0][0])
+    val0[off] = 0.0
+    s0, m0, _ = sb.auction_scale(n, ptr, row, val0)
+    so0, mo0, _ = oscal.auction_scale_sym(n, ptr, row, val0)
+    assert np.array_equal(s0, so0) and np.array_equal(m0, mo0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_equilib_reference_property_on_random_matrices(lib, seed):
+    # spral/tests/scaling.f90:434-452: the infinity norm of every scaled row is within 0.05 of 1
+    rng = np.random.default_rng(200 + seed)
+    n = int(rng.integers(5, 300))
+    ptr, row, val = random_sym(n, 4 * n, rng, wide=bool(seed % 2))
+    s, it = sb.equilib_scale(n, ptr, row, val)
+    so, ito = oscal.inf_norm_equilib_sym(n, ptr, row, val)
+    assert np.array_equal(s, so) and it == ito
+    assert (1.0 - row_inf_norms(n, ptr, row, val, s) <= 0.05).all()
