@@ -67,9 +67,10 @@ typedef struct {
    int nemin;                 /* 32 */
    bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
    long min_gpu_work;
-   int scaling;               /* <=0: none / user supplied in `scale`; 2: auction matching;
-                                 >=4: norm equilibration (MC77-like), both computed at factorize;
-                                 1 (MC64) and 3 (saved matching scaling): flag -98 */
+   int scaling;               /* <=0: none / user supplied in `scale`; 1: Hungarian matching
+                                 (MC64-like); 2: auction matching; >=4: norm equilibration
+                                 (MC77-like), all computed at factorize; 3 (scaling saved by a
+                                 matching ordering): flag -15, orderings are inputs here */
    int pivot_method;          /* 1 APP aggressive, 2 APP block, 3 TPP */
    double small;              /* 1e-20 */
    double u;                  /* 0.01 */
@@ -122,8 +123,8 @@ void spldlt_analyse(int n, int *order, long const *ptr, int const *row,
                     double const *val, void **akeep, bool check,
                     sylver_options_t const *options, sylver_inform_t *inform);
 /* sylver.h:95-98.  val: host or device pointer.  scale (n doubles, original order, may be
- * NULL): read when options->scaling <= 0 (user scaling), written when options->scaling is 2 or
- * >= 4 (the scaling computed here, spldlt_factorize_mod.F90:771-795,804-831; needs ptr/row). */
+ * NULL): read when options->scaling <= 0 (user scaling), written when options->scaling is 1, 2
+ * or >= 4 (the scaling computed here, spldlt_factorize_mod.F90:738-795,804-831; needs ptr/row). */
 void spldlt_factorize(bool posdef, long const *ptr, int const *row,
                       double const *val, double *scale, void *akeep, void **fkeep,
                       sylver_options_t const *options, sylver_inform_t *inform);
@@ -327,6 +328,13 @@ int sylver_b200_equilib_scale(int n, long const *ptr, int const *row, double con
  * inform4 (may be NULL) = { flag, matched, iterations, unmatchable }.  Returns 0, or -1. */
 int sylver_b200_auction_scale(int n, long const *ptr, int const *row, double const *val, double *scaling,
                               int *match, int *inform4);
+/* The scaling of options->scaling == 1: matching-based scaling by the Hungarian algorithm
+ * (MC64-like; hungarian_scale_sym, spral/src/scaling.f90:134-170,596-1325).  match as above
+ * (negative entries complete the matching of a structurally singular matrix, as in the
+ * reference).  inform2 (may be NULL) = { flag, matched }; flag 1 = structurally singular and
+ * scale_if_singular, -2 = structurally singular and not scale_if_singular.  Returns flag. */
+int sylver_b200_hungarian_scale(int n, long const *ptr, int const *row, double const *val, double *scaling,
+                                int *match, int scale_if_singular, int *inform2);
 
 /* Dense single front drivers (reference harness shape:
  * tests/testing_factor_node_indef.hxx:44-460, testing_factor_node_posdef.hxx).

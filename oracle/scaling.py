@@ -227,3 +227,435 @@ def auction_scale_sym(n: int, ptr, row, val):
     scaling = np.array([math.exp((rscaling[i] + cscaling[i]) / 2) for i in range(1, n + 1)])
     return scaling, np.array(match, dtype=np.int32), dict(flag=0, matched=matched, iterations=iterations,
                                                             unmatchable=unmatchable)
+
+
+# ---------------------------------------------------------------------------------------------
+# options%scaling == 1: hungarian_scale_sym (scaling.f90:134-170) -> hungarian_wrapper (:596-801)
+# -> hungarian_match (:938-1194), hungarian_init_heurisitic (:810-929), heap (:1206-1325).
+# Same conventions as the auction restatement above (1-based lists, C library log/exp).
+# ---------------------------------------------------------------------------------------------
+_RINF = _HUGE
+
+
+def _heap_update(idx, Q, val, L):                          # :1206-1239
+    pos = L[idx]
+    if pos <= 1:
+        Q[pos] = idx
+        return
+    v = val[idx]
+    while pos > 1:
+        parent_pos = pos // 2
+        parent_idx = Q[parent_pos]
+        if v >= val[parent_idx]:
+            break
+        Q[pos] = parent_idx
+        L[parent_idx] = pos
+        pos = parent_pos
+    Q[pos] = idx
+    L[idx] = pos
+
+
+def _heap_delete(pos0, qlen, Q, D, L):                     # :1268-1325, returns the new qlen
+    if qlen == pos0:
+        return qlen - 1
+    idx = Q[qlen]
+    v = D[idx]
+    qlen -= 1
+    pos = pos0
+    if pos > 1:
+        while True:
+            parent = pos // 2
+            qk = Q[parent]
+            if v >= D[qk]:
+                break
+            Q[pos] = qk
+            L[qk] = pos
+            pos = parent
+            if pos <= 1:
+                break
+    Q[pos] = idx
+    L[idx] = pos
+    if pos != pos0:
+        return qlen
+    while True:
+        child = 2 * pos
+        if child > qlen:
+            break
+        dk = D[Q[child]]
+        if child < qlen:
+            dr = D[Q[child + 1]]
+            if dk > dr:
+                child += 1
+                dk = dr
+        if v <= dk:
+            break
+        qk = Q[child]
+        Q[pos] = qk
+        L[qk] = pos
+        pos = child
+    Q[pos] = idx
+    L[idx] = pos
+    return qlen
+
+
+def _hungarian_init_heuristic(m, n, ptr, row, val, iperm, jperm, dualu, d, l, search_from):
+    num = 0
+    for i in range(1, m + 1):                              # :838-839
+        dualu[i] = _RINF
+        l[i] = 0
+    for j in range(1, n + 1):                              # :840-848
+        for k in range(ptr[j], ptr[j + 1]):
+            i = row[k]
+            if val[k] > dualu[i]:
+                continue
+            dualu[i] = val[k]
+            iperm[i] = j
+            l[i] = k
+    for i in range(1, m + 1):                              # :852-863
+        j = iperm[i]
+        if j == 0:
+            continue
+        iperm[i] = 0
+        if jperm[j] != 0:
+            continue
+        if (ptr[j + 1] - ptr[j] > m // 10) and (m > 50):
+            continue
+        num += 1
+        iperm[i] = j
+        jperm[j] = l[i]
+    if num == min(m, n):
+        return num
+    for j in range(1, n + 1):                              # :870-871
+        d[j] = 0.0
+        search_from[j] = ptr[j]
+    for j in range(1, n + 1):                              # improve_assign :872-927
+        if jperm[j] != 0:
+            continue
+        if ptr[j] > ptr[j + 1] - 1:
+            continue
+        i0 = row[ptr[j]]
+        vj = val[ptr[j]] - dualu[i0]
+        k0 = ptr[j]
+        for k in range(ptr[j] + 1, ptr[j + 1]):
+            i = row[k]
+            di = val[k] - dualu[i]
+            if di > vj:
+                continue
+            if di == vj and di != _RINF:
+                if iperm[i] != 0 or iperm[i0] == 0:
+                    continue
+            vj = di
+            i0 = i
+            k0 = k
+        d[j] = vj
+        if iperm[i0] == 0:
+            num += 1
+            jperm[j] = k0
+            iperm[i0] = j
+            search_from[j] = k0 + 1
+            continue
+        done = False
+        for k in range(k0, ptr[j + 1]):
+            i = row[k]
+            if (val[k] - dualu[i]) > vj:
+                continue
+            jj = iperm[i]
+            for kk in range(search_from[jj], ptr[jj + 1]):
+                ii = row[kk]
+                if iperm[ii] > 0:
+                    continue
+                if (val[kk] - dualu[ii]) <= d[jj]:
+                    jperm[jj] = kk
+                    iperm[ii] = jj
+                    search_from[jj] = kk + 1
+                    num += 1
+                    jperm[j] = k
+                    iperm[i] = j
+                    search_from[j] = k + 1
+                    done = True
+                    break
+            if done:
+                break
+            search_from[jj] = ptr[jj + 1]
+    return num
+
+
+def _hungarian_match(m, n, ptr, row, val):
+    """Returns (iperm, num, dualu, dualv), all 1-based lists."""
+    jperm = [0] * (n + 1)
+    out = [0] * (n + 1)
+    pr = [0] * (n + 1)
+    q = [0] * (m + 2)
+    longwork = [0] * (m + 1)
+    l = [0] * (m + 1)
+    d = [0.0] * (max(m, n) + 1)
+    iperm = [0] * (m + 1)
+    dualu = [0.0] * (m + 1)
+    dualv = [0.0] * (n + 1)
+    num = _hungarian_init_heuristic(m, n, ptr, row, val, iperm, jperm, dualu, d, longwork, out)
+    if num != min(m, n):
+        for i in range(1, m + 1):                          # :983-984
+            d[i] = _RINF
+            l[i] = 0
+        isp, jsp = -1, -1
+        for jord in range(1, n + 1):                       # :986
+            if jperm[jord] != 0:
+                continue
+            dmin = _RINF
+            qlen = 0
+            low = m + 1
+            up = m + 1
+            csp = _RINF
+            j = jord
+            pr[j] = -1
+            for klong in range(ptr[j], ptr[j + 1]):        # :1004-1018
+                i = row[klong]
+                dnew = val[klong] - dualu[i]
+                if dnew >= csp:
+                    continue
+                if iperm[i] == 0:
+                    csp = dnew
+                    isp = klong
+                    jsp = j
+                else:
+                    if dnew < dmin:
+                        dmin = dnew
+                    d[i] = dnew
+                    qlen += 1
+                    longwork[qlen] = klong
+            q0 = qlen
+            qlen = 0
+            for kk in range(1, q0 + 1):                    # :1022-1043
+                klong = longwork[kk]
+                i = row[klong]
+                if csp <= d[i]:
+                    d[i] = _RINF
+                    continue
+                if d[i] <= dmin:
+                    low -= 1
+                    q[low] = i
+                    l[i] = low
+                else:
+                    qlen += 1
+                    l[i] = qlen
+                    _heap_update(i, q, d, l)
+                jj = iperm[i]
+                out[jj] = klong
+                pr[jj] = j
+            for _jdum in range(1, num + 1):                # :1045
+                if low == up:
+                    if qlen == 0:
+                        break
+                    i = q[1]
+                    if d[i] >= csp:
+                        break
+                    dmin = d[i]
+                    while qlen > 0:
+                        i = q[1]
+                        if d[i] > dmin:
+                            break
+                        i = q[1]
+                        qlen = _heap_delete(1, qlen, q, d, l)      # heap_pop
+                        low -= 1
+                        q[low] = i
+                        l[i] = low
+                q0 = q[up - 1]
+                dq0 = d[q0]
+                if dq0 >= csp:
+                    break
+                up -= 1
+                j = iperm[q0]
+                vj = dq0 - val[jperm[j]] + dualu[q0]
+                for klong in range(ptr[j], ptr[j + 1]):    # :1072-1110
+                    i = row[klong]
+                    if l[i] >= up:
+                        continue
+                    dnew = vj + val[klong] - dualu[i]
+                    if dnew >= csp:
+                        continue
+                    if iperm[i] == 0:
+                        csp = dnew
+                        isp = klong
+                        jsp = j
+                    else:
+                        di = d[i]
+                        if di <= dnew:
+                            continue
+                        if l[i] >= low:
+                            continue
+                        d[i] = dnew
+                        if dnew <= dmin:
+                            lpos = l[i]
+                            if lpos != 0:
+                                qlen = _heap_delete(lpos, qlen, q, d, l)
+                            low -= 1
+                            q[low] = i
+                            l[i] = low
+                        else:
+                            if l[i] == 0:
+                                qlen += 1
+                                l[i] = qlen
+                            _heap_update(i, q, d, l)
+                        jj = iperm[i]
+                        out[jj] = klong
+                        pr[jj] = j
+            if csp != _RINF:                               # :1114-1135
+                num += 1
+                i = row[isp]
+                iperm[i] = jsp
+                jperm[jsp] = isp
+                j = jsp
+                for _jdum in range(1, num + 1):
+                    jj = pr[j]
+                    if jj == -1:
+                        break
+                    klong = out[j]
+                    i = row[klong]
+                    iperm[i] = jj
+                    jperm[jj] = klong
+                    j = jj
+                for kk in range(up, m + 1):
+                    i = q[kk]
+                    dualu[i] = dualu[i] + d[i] - csp
+            for kk in range(low, m + 1):                   # 190 :1136-1145
+                i = q[kk]
+                d[i] = _RINF
+                l[i] = 0
+            for kk in range(1, qlen + 1):
+                i = q[kk]
+                d[i] = _RINF
+                l[i] = 0
+    for j in range(1, n + 1):                              # 1000 :1152-1159
+        klong = jperm[j]
+        dualv[j] = val[klong] - dualu[row[klong]] if klong != 0 else 0.0
+    for i in range(1, m + 1):
+        if iperm[i] == 0:
+            dualu[i] = 0.0
+    if num == min(m, n):
+        return iperm, num, dualu, dualv
+    jperm = [0] * (n + 1)                                  # :1169-1193
+    k = 0
+    for i in range(1, m + 1):
+        if iperm[i] == 0:
+            k += 1
+            out[k] = i
+        else:
+            jperm[iperm[i]] = i
+    k = 0
+    for j in range(1, n + 1):
+        if jperm[j] != 0:
+            continue
+        k += 1
+        iperm[out[k]] = -j
+    return iperm, num, dualu, dualv
+
+
+def hungarian_scale_sym(n: int, ptr, row, val, scale_if_singular: bool = False):
+    """Lower triangle CSC, 1-based ptr/row.  Returns (scaling, match, inform dict)."""
+    ptr = [0] + [int(x) for x in ptr[: n + 1]]
+    m = n
+    ne = 2 * (ptr[n + 1] - 1)
+    ptr2 = [0] * (n + 2)
+    row2 = [0] * (ne + 1)
+    val2 = [0.0] * (ne + 1)
+    cmax = [0.0] * (n + 1)
+    k = 1
+    for i in range(1, n + 1):                              # :637-649
+        ptr2[i] = k
+        for j in range(ptr[i], ptr[i + 1]):
+            if val[j - 1] == 0.0:
+                continue
+            row2[k] = int(row[j - 1])
+            val2[k] = abs(float(val[j - 1]))
+            k += 1
+        for j in range(ptr2[i], k):
+            val2[j] = math.log(val2[j])
+    ptr2[n + 1] = k
+    _half_to_full(n, row2, ptr2, val2)
+    for i in range(1, n + 1):                              # :653-657
+        colmax = max(val2[ptr2[i]:ptr2[i + 1]]) if ptr2[i + 1] > ptr2[i] else -_HUGE
+        cmax[i] = colmax
+        for j in range(ptr2[i], ptr2[i + 1]):
+            val2[j] = colmax - val2[j]
+    match, matched, dualu, dualv = _hungarian_match(m, n, ptr2, row2, val2)
+    flag = 0
+    if matched != min(m, n):                               # :666-677
+        flag = 1 if scale_if_singular else -2
+    rscaling = [0.0] * (m + 1)
+    cscaling = [0.0] * (n + 1)
+    if matched == n:                                       # :679-686
+        for i in range(1, m + 1):
+            rscaling[i] = dualu[i]
+        for i in range(1, n + 1):
+            cscaling[i] = dualv[i] - cmax[i]
+        if n > 0:                                          # match_postproc, square
+            rsum = 0.0
+            for i in range(1, m + 1):
+                rsum += rscaling[i]
+            csum = 0.0
+            for i in range(1, n + 1):
+                csum += cscaling[i]
+            adjust = (rsum / n - csum / n) / 2
+            for i in range(1, m + 1):
+                rscaling[i] = rscaling[i] - adjust
+            for i in range(1, n + 1):
+                cscaling[i] = cscaling[i] + adjust
+    else:                                                  # :688-800
+        old_to_new = [0] * (n + 1)
+        new_to_old = [0] * (n + 1)
+        j = matched + 1
+        k = 0
+        for i in range(1, m + 1):
+            if match[i] < 0:
+                old_to_new[i] = -j
+                j += 1
+            else:
+                k += 1
+                old_to_new[i] = k
+                new_to_old[k] = i
+        nent = 0
+        k = 0
+        ptr2[1] = 1
+        j2 = 1
+        for i in range(1, n + 1):
+            j1 = j2
+            j2 = ptr2[i + 1]
+            if match[i] < 0:
+                continue
+            k += 1
+            for jl in range(j1, j2):
+                jj = row2[jl]
+                if match[jj] < 0:
+                    continue
+                nent += 1
+                row2[nent] = old_to_new[jj]
+                val2[nent] = val2[jl]
+            ptr2[k + 1] = nent + 1
+        nn = k
+        cperm, matched, dualu, dualv = _hungarian_match(nn, nn, ptr2, row2, val2)
+        for i in range(1, n + 1):
+            jn = old_to_new[i]
+            rscaling[i] = -_HUGE if jn < 0 else (dualu[jn] + dualv[jn] - cmax[i]) / 2
+        match = [-1] * (n + 1)
+        for i in range(1, nn + 1):
+            match[new_to_old[i]] = cperm[i]
+        for i in range(1, n + 1):
+            if match[i] == -1:
+                match[i] = old_to_new[i]
+        cscale = list(rscaling)
+        for i in range(1, n + 1):
+            for jl in range(ptr[i], ptr[i + 1]):
+                kr = int(row[jl - 1])
+                a = abs(float(val[jl - 1]))
+                lg = math.log(a) if a > 0 else -math.inf
+                if cscale[i] == -_HUGE and cscale[kr] != -_HUGE:
+                    rscaling[i] = max(rscaling[i], lg + rscaling[kr])
+                if cscale[kr] == -_HUGE and cscale[i] != -_HUGE:
+                    rscaling[kr] = max(rscaling[kr], lg + rscaling[i])
+        for i in range(1, n + 1):
+            if cscale[i] != -_HUGE:
+                continue
+            rscaling[i] = 0.0 if rscaling[i] == -_HUGE else -rscaling[i]
+        cscaling = list(rscaling)
+    scaling = np.array([math.exp((rscaling[i] + cscaling[i]) / 2) for i in range(1, n + 1)])
+    return scaling, np.array(match[1:], dtype=np.int32), dict(flag=flag, matched=matched)

@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale", "sylver_b200_auction_scale",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale",
 ]
 
 
@@ -159,6 +159,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_plan_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.sylver_b200_equilib_scale.argtypes = [C.c_int, vp, vp, vp, vp]
     L.sylver_b200_auction_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp]
+    L.sylver_b200_hungarian_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -280,6 +281,22 @@ def auction_scale(n: int, ptr, row, val):
     if lib().sylver_b200_auction_scale(n, _ptr(ptr), _ptr(row), _ptr(val), _ptr(sc), _ptr(match), _ptr(inf)) != 0:
         raise RuntimeError("sylver_b200_auction_scale failed")
     return sc[:n], match[:n], dict(flag=int(inf[0]), matched=int(inf[1]), iterations=int(inf[2]), unmatchable=int(inf[3]))
+
+
+def hungarian_scale(n: int, ptr, row, val, scale_if_singular: bool = False):
+    """Hungarian (MC64-like) scaling of a lower-triangle CSC matrix
+    (sylver_b200_hungarian_scale): (scaling, match, inform dict)."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    row = np.ascontiguousarray(row, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    sc = np.zeros(max(n, 1))
+    match = np.zeros(max(n, 1), dtype=np.int32)
+    inf = np.zeros(2, dtype=np.int32)
+    flag = lib().sylver_b200_hungarian_scale(n, _ptr(ptr), _ptr(row), _ptr(val), _ptr(sc), _ptr(match),
+                                             1 if scale_if_singular else 0, _ptr(inf))
+    if flag == -1:
+        raise RuntimeError("sylver_b200_hungarian_scale failed")
+    return sc[:n], match[:n], dict(flag=int(inf[0]), matched=int(inf[1]))
 
 
 def plan_split(solver: "Solver", rank: int, world: int):

@@ -188,23 +188,33 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
    if (!options->action && n != ak->inform.matrix_rank) { inform->flag = SYLVER_ERROR_SINGULAR; fk->inform = *inform; return; }
    if (ak->sym.nnodes == 0) { inform->flag = SYLVER_SUCCESS; inform->matrix_rank = 0; fk->inform = *inform; return; }
    if (!val) { inform->flag = SYLVER_ERROR_VAL; fk->inform = *inform; return; }
-   if (options->scaling == 1 || options->scaling == 3) {
-      // MC64 (1) and the matching-order scaling saved by analyse (3) are pre-processing outside
-      // this path; a scaling computed elsewhere can be passed in `scale`
-      inform->flag = SYLVER_ERROR_UNIMPLEMENTED;
+   if (options->scaling == 3) {
+      // the scaling saved by a matching-based ORDERING at analyse: orderings are inputs here
+      // (options.ordering must be 0), so there is never a saved scaling
+      // (spldlt_factorize_mod.F90:797-802)
+      inform->flag = SYLVER_ERROR_NO_SAVED_SCALING;
       fk->inform = *inform;
       return;
    }
    const bool had_scaling = !fk->scaling.empty();
    fk->scaling.clear();
-   if (options->scaling == 2 || options->scaling >= 4) {
-      // computed here: auction matching (2, spldlt_factorize_mod.F90:771-795) or norm
-      // equilibration (>= 4, :804-831); permuted to elimination order, handed back in `scale`
+   if (options->scaling > 0) {
+      // computed here: Hungarian matching (1, spldlt_factorize_mod.F90:738-769), auction matching
+      // (2, :771-795) or norm equilibration (>= 4, :804-831); permuted to elimination order,
+      // handed back in `scale`
       if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; fk->inform = *inform; return; }
       std::vector<double> tmp, scaling(n);
       const double* hval = values_on_host(val, (size_t)(ptr[n] - 1), tmp);
       if (!hval) { inform->flag = SYLVER_ERROR_CUDA_UNKNOWN; fk->inform = *inform; return; }
-      if (options->scaling == 2) {
+      if (options->scaling == 1) {
+         // hsoptions%scale_if_singular = options%action; -2: structurally singular and !action
+         const int hf = hungarian_scale_sym(n, ptr, row, hval, scaling.data(), nullptr, options->action, nullptr);
+         if (hf == -1 || hf == -2) {
+            inform->flag = hf == -1 ? SYLVER_ERROR_ALLOCATION : SYLVER_ERROR_SINGULAR;
+            fk->inform = *inform;
+            return;
+         }
+      } else if (options->scaling == 2) {
          if (auction_scale_sym(n, ptr, row, hval, scaling.data(), nullptr, nullptr) != 0) {
             inform->flag = SYLVER_ERROR_ALLOCATION;
             fk->inform = *inform;
@@ -484,6 +494,15 @@ int sylver_b200_auction_scale(int n, long const* ptr, int const* row, double con
    AuctionInform inf;
    const int flag = auction_scale_sym(n, ptr, row, val, scaling, match, &inf);
    if (inform4) { inform4[0] = inf.flag; inform4[1] = inf.matched; inform4[2] = inf.iterations; inform4[3] = inf.unmatchable; }
+   return flag;
+}
+
+int sylver_b200_hungarian_scale(int n, long const* ptr, int const* row, double const* val, double* scaling,
+                                int* match, int scale_if_singular, int* inform2) {
+   if (n < 0 || !ptr || !row || !val || !scaling) return -1;
+   HungarianInform inf;
+   const int flag = hungarian_scale_sym(n, ptr, row, val, scaling, match, scale_if_singular != 0, &inf);
+   if (inform2) { inform2[0] = inf.flag; inform2[1] = inf.matched; }
    return flag;
 }
 

@@ -23,4 +23,16 @@ struct AuctionInform {
 int auction_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling, int* match,
                       AuctionInform* inform);
 
+// options%scaling == 1: matching-based scaling by the Hungarian algorithm (MC64-like):
+// hungarian_scale_sym (scaling.f90:134-170) -> hungarian_wrapper (:596-801) ->
+// hungarian_match (:938-1194) with hungarian_init_heurisitic (:810-929) and the heap (:1206-1325).
+struct HungarianInform {
+   int flag = 0;      // 0, 1 = WARNING_SINGULAR, -1 allocation, -2 = ERROR_SINGULAR
+   int matched = 0;
+};
+// match (n ints, may be null): match[i] = column (1-based) matched to row i+1; for a structurally
+// singular matrix the unmatched rows hold negative values as in the reference.
+int hungarian_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling, int* match,
+                        bool scale_if_singular, HungarianInform* inform);
+
 }  // namespace sylver_b200

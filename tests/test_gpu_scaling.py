@@ -1,5 +1,6 @@
 """Scaled factorizations on the GPU: options.scaling >= 4 (norm
-equilibration) and == 2 (auction matching), both computed at factorize, and a user-supplied scaling.  The matrices are Laplacian /
+equilibration), == 2 (auction matching) and == 1 (Hungarian matching), all computed at factorize,
+and a user-supplied scaling.  The matrices are Laplacian /
 KKT systems with rows and columns scaled by 10^U(-4,4): the scaled backward error of the solve
 must be <= 1e-14 and within 10x of the SSIDS CPU oracle run with the same scaling vector."""
 import numpy as np
@@ -17,7 +18,7 @@ def _order(kind, k):
     return gen.nested_dissection_order(k, dofs_per_cell=4) if kind == "kkt" else gen.nested_dissection_order(k)
 
 
-@pytest.mark.parametrize("mode", [4, 2], ids=["equilib", "auction"])
+@pytest.mark.parametrize("mode", [4, 2, 1], ids=["equilib", "auction", "hungarian"])
 @pytest.mark.parametrize("kind,k,posdef", [("lap27", 10, True), ("lap7", 14, True), ("lap7", 14, False), ("kkt", 8, False)])
 def test_scaled_factorization(lib, oracle_ref, kind, k, posdef, mode):
     sb.require_gpu()
@@ -31,7 +32,7 @@ def test_scaled_factorization(lib, oracle_ref, kind, k, posdef, mode):
     inf = s.factorize(val, posdef=posdef, scale=scale)
     assert inf.flag >= 0, inf.flag
     # the scaling handed back is the one the host routine computes (original order)
-    sc = sb.equilib_scale(n, ptr, row, val)[0] if mode == 4 else sb.auction_scale(n, ptr, row, val)[0]
+    sc = {4: sb.equilib_scale, 2: sb.auction_scale, 1: sb.hungarian_scale}[mode](n, ptr, row, val)[0]
     assert np.array_equal(scale, sc)
     x = s.solve(b)
     be = gen.backward_error(n, ptr, row, val, x, b)

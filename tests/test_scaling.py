@@ -62,14 +62,13 @@ def test_equilib_edge_cases(lib):
 
 
 def test_scaling_options_are_rejected_or_accepted(lib):
-    """1 and 3 (MC64, saved matching scaling) stay outside this path: flag -98 without a GPU
-    being touched."""
+    """3 (the scaling saved by a matching-based ordering at analyse) cannot exist here, orderings
+    being inputs: the reference's own error for that case, without a GPU being touched."""
     n, ptr, row, val = gen.laplacian_7pt(4)
     s = sb.Solver()
     assert s.analyse(n, ptr, row, gen.nested_dissection_order(4)).flag == 0
-    for sc in (1, 3):
-        s.options.scaling = sc
-        assert s.factorize(val, posdef=True).flag == -98
+    s.options.scaling = 3
+    assert s.factorize(val, posdef=True).flag == -15       # SYLVER_ERROR_NO_SAVED_SCALING
     s.free()
 
 
@@ -173,3 +172,94 @@ def test_equilib_reference_property_on_random_matrices(lib, seed):
     so, ito = oscal.inf_norm_equilib_sym(n, ptr, row, val)
     assert np.array_equal(s, so) and it == ito
     assert (1.0 - row_inf_norms(n, ptr, row, val, s) <= 0.05).all()
+
+
+ERR_TOL = 5e-14          # spral/tests/scaling.f90:14
+
+
+def check_hungarian_properties(n, ptr, row, val, scaling, match):
+    # spral/tests/scaling.f90:613-640: a perfect matching on entries of the matrix
+    assert ((match >= 1) & (match <= n)).all()
+    assert np.array_equal(np.sort(match), np.arange(1, n + 1))
+    ent = set()
+    for j in range(n):
+        for k in range(ptr[j] - 1, ptr[j + 1] - 1):
+            ent.add((int(row[k]), j + 1))
+            ent.add((j + 1, int(row[k])))
+    assert all((i + 1, int(match[i])) in ent for i in range(n))
+    # :645-662: every scaled entry <= 1, every row attains 1 (the optimality of the matching)
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    assert (np.abs(scaling[row - 1] * val * scaling[col]) < 1.0 + ERR_TOL).all()
+    assert (row_inf_norms(n, ptr, row, val, scaling) >= 1.0 - ERR_TOL).all()
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_hungarian_matches_restatement_and_reference_properties(lib, seed):
+    rng = np.random.default_rng(300 + seed)
+    n = seed + 1 if seed < 6 else int(rng.integers(20, 200))         # very small problems first, as the reference
+    nza = n + int(rng.integers(0, max(n * n // 10 - n, 0) + 1))
+    ptr, row, val = random_sym(n, nza, rng, wide=bool(seed % 2))
+    s, m, inf = sb.hungarian_scale(n, ptr, row, val)
+    so, mo, info = oscal.hungarian_scale_sym(n, ptr, row, val)
+    assert inf == info and inf["flag"] == 0 and inf["matched"] == n
+    assert np.array_equal(m, mo)
+    assert np.array_equal(s, so)
+    check_hungarian_properties(n, ptr, row, val, s, m)
+
+
+@pytest.mark.parametrize("kind,k,seed", [("lap7", 8, 1), ("lap27", 6, 2), ("kkt", 6, 3)])
+def test_hungarian_on_the_benchmark_families(lib, kind, k, seed):
+    n, ptr, row, val = badly_scaled(kind, k, seed)
+    s, m, inf = sb.hungarian_scale(n, ptr, row, val)
+    so, mo, info = oscal.hungarian_scale_sym(n, ptr, row, val)
+    assert inf == info and np.array_equal(m, mo) and np.array_equal(s, so)
+    check_hungarian_properties(n, ptr, row, val, s, m)
+
+
+def structurally_singular(n, rng, nempty):
+    """Random symmetric matrix whose last `nempty` rows/columns are empty, and whose first
+    diagonal entries are missing (off-diagonal matching needed)."""
+    ptr, row, val = random_sym(n - nempty, 3 * (n - nempty), rng)
+    ptr = np.concatenate([ptr, np.full(nempty, ptr[-1], dtype=np.int64)])
+    return ptr, row, val
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_hungarian_structurally_singular(lib, seed):
+    """The rank-deficient branch of hungarian_wrapper (scaling.f90:688-800): matching on the
+    full-rank part, Duff-Pralet scaling of the rest; flag 1 with scale_if_singular (what
+    options.action = true selects), -2 without."""
+    rng = np.random.default_rng(400 + seed)
+    n = int(rng.integers(8, 80))
+    nempty = int(rng.integers(1, 4))
+    ptr, row, val = structurally_singular(n, rng, nempty)
+    s, m, inf = sb.hungarian_scale(n, ptr, row, val, scale_if_singular=True)
+    so, mo, info = oscal.hungarian_scale_sym(n, ptr, row, val, scale_if_singular=True)
+    assert inf == info and inf["flag"] == 1 and inf["matched"] == n - nempty
+    assert np.array_equal(m, mo) and np.array_equal(s, so)
+    assert (m[n - nempty:] < 0).all() and (m[: n - nempty] >= 1).all()
+    assert np.array_equal(s[n - nempty:], np.ones(nempty))          # isolated rows: scaling 1
+    # the matched part satisfies the same optimality property
+    k = n - nempty
+    check_hungarian_properties(k, ptr[: k + 1], row, val, s[:k], m[:k])
+    s2, m2, inf2 = sb.hungarian_scale(n, ptr, row, val, scale_if_singular=False)
+    assert inf2["flag"] == -2
+    assert oscal.hungarian_scale_sym(n, ptr, row, val, scale_if_singular=False)[2]["flag"] == -2
+
+
+def test_hungarian_rank_deficient_with_entries(lib):
+    """Structurally singular although no row is empty: three rows that only see one column.
+    Arrow-like pattern: rows 2,3,4 have entries only in column 1 (and no diagonal)."""
+    #     [ 2  1  1  1 ]
+    # A = [ 1  0  0  0 ]    structural rank 2
+    #     [ 1  0  0  0 ]
+    #     [ 1  0  0  0 ]
+    ptr = np.array([1, 5, 5, 5, 5], dtype=np.int64)
+    row = np.array([1, 2, 3, 4], dtype=np.int32)
+    val = np.array([2.0, 1.0, 4.0, 0.5])
+    s, m, inf = sb.hungarian_scale(4, ptr, row, val, scale_if_singular=True)
+    so, mo, info = oscal.hungarian_scale_sym(4, ptr, row, val, scale_if_singular=True)
+    assert inf == info and inf["flag"] == 1
+    assert np.array_equal(m, mo) and np.array_equal(s, so)
+    assert np.isfinite(s).all() and (s > 0).all()
+    assert (m < 0).sum() == 2
