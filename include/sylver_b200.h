@@ -118,7 +118,10 @@ void sylver_finalize(void);
 /* sylver.h:77 */
 void sylver_default_options(sylver_options_t *options);
 /* sylver.h:79-83 ; options->ordering must be 0 (order supplied), order is
- * overwritten with the final elimination order. */
+ * overwritten with the final elimination order.  check = true: the matrix is cleaned first
+ * (out-of-range entries dropped, duplicates summed: inform->matrix_outrange / matrix_dup, warning
+ * flags 1..5, errors -3 / -4 as the reference); spldlt_factorize then maps the caller's val
+ * through the saved conversion map.  check = false: the matrix must be a clean lower triangle. */
 void spldlt_analyse(int n, int *order, long const *ptr, int const *row,
                     double const *val, void **akeep, bool check,
                     sylver_options_t const *options, sylver_inform_t *inform);
@@ -316,6 +319,22 @@ int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *o
  * offset and count (doubles, inside the front's contribution block), direction (0 send, 1
  * receive).  Returns the number of pieces. */
 int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
+
+/* What spldlt_analyse(check = true) does to the matrix, on its own (host only): SPRAL's
+ * clean_cscl_oop for a symmetric indefinite matrix (spral/src/matrix_util.f90:1024-1398):
+ * entries above the diagonal or outside 1..n are dropped, duplicates are summed, rows are
+ * sorted.  ptr_out: n+1 longs; row_out: cap ints; map: 2*cap longs -- map[0:ne] is the 1-based
+ * source entry of every cleaned entry, followed by (destination, source) pairs of the
+ * duplicates to add.  counts5 = { flag, out-of-range entries, duplicates as the reference
+ * counts them, ne, length of map }.  Returns flag: 0, a warning 1..5 (SYLVER_WARNING_IDX_OOR
+ * .. MISS_DIAG_OORDUP) or matrix_util's error (-5/-6 bad ptr, -10 a column with only
+ * out-of-range entries). */
+int sylver_b200_clean_matrix(int n, long const *ptr, int const *row, int cap, long *ptr_out, int *row_out,
+                             long *map, long *counts5);
+
+/* Values of the cleaned matrix from the caller's values through that map (what
+ * spldlt_factorize does after a checked analyse; apply_conversion_map, matrix_util.f90:2559). */
+int sylver_b200_apply_conversion_map(long ne, long lmap, long const *map, double const *val, double *val_out);
 
 /* The scaling spldlt_factorize computes for options->scaling >= 4, on its own (host only):
  * symmetric infinity-norm equilibration of the lower-triangle CSC matrix (1-based ptr/row),

@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale", "sylver_b200_clean_matrix", "sylver_b200_apply_conversion_map",
 ]
 
 
@@ -160,6 +160,8 @@ def lib() -> C.CDLL:
     L.sylver_b200_equilib_scale.argtypes = [C.c_int, vp, vp, vp, vp]
     L.sylver_b200_auction_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp]
     L.sylver_b200_hungarian_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.sylver_b200_clean_matrix.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.sylver_b200_apply_conversion_map.argtypes = [C.c_long, C.c_long, vp, vp, vp]
     L.sylver_b200_bench_dmma.restype = C.c_double
     L.sylver_b200_bench_dmma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.sylver_b200_bench_copy.restype = C.c_double
@@ -281,6 +283,33 @@ def auction_scale(n: int, ptr, row, val):
     if lib().sylver_b200_auction_scale(n, _ptr(ptr), _ptr(row), _ptr(val), _ptr(sc), _ptr(match), _ptr(inf)) != 0:
         raise RuntimeError("sylver_b200_auction_scale failed")
     return sc[:n], match[:n], dict(flag=int(inf[0]), matched=int(inf[1]), iterations=int(inf[2]), unmatchable=int(inf[3]))
+
+
+def clean_matrix(n: int, ptr, row):
+    """What analyse(check=True) does to the structure (sylver_b200_clean_matrix):
+    dict(flag, noor, ndup, ptr, row, map)."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    row = np.ascontiguousarray(row, dtype=np.int32)
+    cap = max(len(row), 1)
+    po = np.zeros(max(n, 0) + 1, dtype=np.int64)
+    ro = np.zeros(cap, dtype=np.int32)
+    mp = np.zeros(2 * cap, dtype=np.int64)
+    cnt = np.zeros(5, dtype=np.int64)
+    flag = lib().sylver_b200_clean_matrix(n, _ptr(ptr), _ptr(row), cap, _ptr(po), _ptr(ro), _ptr(mp), _ptr(cnt))
+    if flag < 0:
+        return dict(flag=flag)
+    return dict(flag=flag, noor=int(cnt[1]), ndup=int(cnt[2]), ptr=po, row=ro[: cnt[3]], map=mp[: cnt[4]])
+
+
+def apply_conversion_map(cm: dict, val) -> np.ndarray:
+    """Values of the cleaned matrix `cm` (from clean_matrix) for the caller's values."""
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    mp = np.ascontiguousarray(cm["map"], dtype=np.int64)
+    ne = len(cm["row"])
+    out = np.zeros(max(ne, 1))
+    if lib().sylver_b200_apply_conversion_map(ne, len(mp), _ptr(mp), _ptr(val), _ptr(out)) != 0:
+        raise RuntimeError("sylver_b200_apply_conversion_map failed")
+    return out[:ne]
 
 
 def hungarian_scale(n: int, ptr, row, val, scale_if_singular: bool = False):

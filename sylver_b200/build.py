@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsylver_b200.so")
 
-SOURCES = ["api.cpp", "analyse.cpp", "scaling.cpp", "partition.cpp", "comm.cpp", "engine.cu", "engine_indef.cu", "aux.cu"]
+SOURCES = ["api.cpp", "analyse.cpp", "scaling.cpp", "clean.cpp", "partition.cpp", "comm.cpp", "engine.cu", "engine_indef.cu", "aux.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",

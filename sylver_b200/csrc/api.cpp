@@ -13,6 +13,7 @@
 #include "../../include/sylver_b200.h"
 #include "analyse.hpp"
 #include "comm.hpp"
+#include "clean.hpp"
 #include "engine.hpp"
 #include "scaling.hpp"
 
@@ -29,6 +30,8 @@ struct AKeep {
    SymbolicTree* tree = nullptr;
    sylver_inform_t inform{};
    bool analysed = false;
+   bool check = false;        // analyse(check = true): the matrix below replaces the caller's
+   CleanMatrix clean;         // cleaned structure + conversion map (akeep%ptr/row/map/lmap)
 };
 
 struct FKeep {
@@ -119,7 +122,6 @@ void sylver_default_options(sylver_options_t* o) {
 void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double const* val, void** akeep_p,
                     bool check, sylver_options_t const* options, sylver_inform_t* inform) {
    (void)val;
-   (void)check;   // matrix cleaning (check=true) is a pre-processing step outside this path
    *inform = inform_default();
    AKeep* ak = static_cast<AKeep*>(*akeep_p);
    if (!ak) {
@@ -130,7 +132,9 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       if (ak->tree) { symbolic_tree_forget(ak->tree); delete ak->tree; ak->tree = nullptr; }
       ak->sym = Symbolic();
       ak->analysed = false;
+      ak->clean = CleanMatrix();
    }
+   ak->check = check;
    if (n < 0) { inform->flag = SYLVER_ERROR_A_N_OOR; ak->inform = *inform; return; }
    if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; ak->inform = *inform; return; }
    if (options->ordering < 0 || options->ordering > 2) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
@@ -141,6 +145,22 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       return;
    }
    if (n > 0 && !order) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
+   if (check) {
+      // out-of-range entries dropped, duplicates summed, rows sorted; warnings keep matrix_util's
+      // numbering (src/spldlt_analyse_mod.F90:707-739)
+      const int mu_flag = clean_cscl_oop_sym_indef(n, ptr, row, ak->clean);
+      if (mu_flag < 0) {
+         inform->flag = mu_flag == -1 ? SYLVER_ERROR_ALLOCATION
+                                      : (mu_flag == -10 ? SYLVER_ERROR_A_ALL_OOR : SYLVER_ERROR_A_PTR);
+         ak->inform = *inform;
+         return;
+      }
+      inform->matrix_outrange = ak->clean.noor;
+      inform->matrix_dup = ak->clean.ndup;
+      ptr = ak->clean.ptr.data();
+      row = ak->clean.row.data();
+   }
+   const int clean_flag = check ? ak->clean.flag : 0;
    int flag;
    try {
       flag = analyse(n, ptr, row, order, options->nemin, ak->sym);
@@ -148,7 +168,7 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       flag = ANAL_ERROR_ALLOCATION;
    }
    if (flag < 0) { inform->flag = flag; ak->inform = *inform; return; }
-   inform->flag = flag;
+   inform->flag = flag > 0 ? flag : clean_flag;      // the singularity warning replaces a cleaning warning (:805-810)
    Symbolic& s = ak->sym;
    if (n > 0) {
       int tflag = 0;
@@ -188,6 +208,20 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
    if (!options->action && n != ak->inform.matrix_rank) { inform->flag = SYLVER_ERROR_SINGULAR; fk->inform = *inform; return; }
    if (ak->sym.nnodes == 0) { inform->flag = SYLVER_SUCCESS; inform->matrix_rank = 0; fk->inform = *inform; return; }
    if (!val) { inform->flag = SYLVER_ERROR_VAL; fk->inform = *inform; return; }
+   // analyse(check = true): a clean copy of the values through the conversion map
+   // (apply_conversion_map, src/spldlt_factorize_mod.F90:672-679); the structure is akeep's
+   std::vector<double> val_clean, val_host_tmp;
+   if (ak->check) {
+      long nin = 0;
+      for (long i = 0; i < ak->clean.lmap; ++i) nin = std::max(nin, ak->clean.map[i]);
+      const double* hval = values_on_host(val, (size_t)nin, val_host_tmp);
+      if (!hval) { inform->flag = SYLVER_ERROR_CUDA_UNKNOWN; fk->inform = *inform; return; }
+      val_clean.resize(ak->clean.row.size() + 1);
+      apply_conversion_map(ak->clean, hval, val_clean.data());
+      val = val_clean.data();
+      ptr = ak->clean.ptr.data();
+      row = ak->clean.row.data();
+   }
    if (options->scaling == 3) {
       // the scaling saved by a matching-based ORDERING at analyse: orderings are inputs here
       // (options.ordering must be 0), so there is never a saved scaling
@@ -495,6 +529,30 @@ int sylver_b200_auction_scale(int n, long const* ptr, int const* row, double con
    const int flag = auction_scale_sym(n, ptr, row, val, scaling, match, &inf);
    if (inform4) { inform4[0] = inf.flag; inform4[1] = inf.matched; inform4[2] = inf.iterations; inform4[3] = inf.unmatchable; }
    return flag;
+}
+
+int sylver_b200_clean_matrix(int n, long const* ptr, int const* row, int cap, long* ptr_out, int* row_out,
+                             long* map, long* counts5) {
+   if (!ptr || !row || !counts5) return -99;
+   CleanMatrix cm;
+   const int flag = clean_cscl_oop_sym_indef(n, ptr, row, cm);
+   counts5[0] = flag; counts5[1] = cm.noor; counts5[2] = cm.ndup;
+   counts5[3] = (long)cm.row.size(); counts5[4] = cm.lmap;
+   if (flag < 0) return flag;
+   if (ptr_out) std::copy(cm.ptr.begin(), cm.ptr.end(), ptr_out);
+   if (row_out && (long)cm.row.size() <= cap) std::copy(cm.row.begin(), cm.row.end(), row_out);
+   if (map && cm.lmap <= 2L * cap) std::copy(cm.map.begin(), cm.map.end(), map);
+   return flag;
+}
+
+int sylver_b200_apply_conversion_map(long ne, long lmap, long const* map, double const* val, double* val_out) {
+   if (ne < 0 || lmap < ne || !map || !val || !val_out) return -1;
+   CleanMatrix cm;
+   cm.row.resize((size_t)ne);
+   cm.map.assign(map, map + lmap);
+   cm.lmap = lmap;
+   apply_conversion_map(cm, val, val_out);
+   return 0;
 }
 
 int sylver_b200_hungarian_scale(int n, long const* ptr, int const* row, double const* val, double* scaling,

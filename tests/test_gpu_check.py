@@ -1,0 +1,71 @@
+"""spldlt_analyse(check=True) end to end on the GPU: a Laplacian / KKT matrix made dirty
+(duplicates that sum to the original entries exactly, entries above the diagonal, rows outside
+1..n, shuffled columns) must be factorized and solved exactly like the clean matrix -- the
+cleaned structure is the clean matrix and the conversion map reproduces its values bit for bit."""
+import numpy as np
+import pytest
+
+import sylver_b200 as sb
+from sylver_b200 import gen
+
+pytestmark = pytest.mark.gpu
+
+
+def make_dirty(n, ptr, row, val, rng):
+    p = [1]
+    rows, vals = [], []
+    for j in range(n):
+        r = list(row[ptr[j] - 1: ptr[j + 1] - 1])
+        v = list(val[ptr[j] - 1: ptr[j + 1] - 1])
+        for t in range(len(r)):
+            if rng.random() < 0.3:                 # split an entry into two exact halves
+                v[t] *= 0.5
+                r.append(r[t]); v.append(v[t])
+        if j > 0 and rng.random() < 0.4:           # an entry above the diagonal
+            r.append(int(rng.integers(1, j + 1))); v.append(99.0)
+        if rng.random() < 0.2:                     # rows outside 1..n
+            r.append(n + 1 + int(rng.integers(0, 3))); v.append(-7.0)
+            r.append(0); v.append(5.0)
+        perm = rng.permutation(len(r))
+        rows += [r[i] for i in perm]
+        vals += [v[i] for i in perm]
+        p.append(p[-1] + len(r))
+    return np.array(p, dtype=np.int64), np.array(rows, dtype=np.int32), np.array(vals)
+
+
+@pytest.mark.parametrize("kind,k,posdef", [("lap7", 8, True), ("lap27", 6, True), ("kkt", 5, False)])
+def test_checked_matrix_is_factorized_like_the_clean_one(lib, kind, k, posdef):
+    sb.require_gpu()
+    if kind == "kkt":
+        n, ptr, row, val = gen.stokes_kkt(k)
+        order = gen.nested_dissection_order(k, dofs_per_cell=4)
+    else:
+        n, ptr, row, val = (gen.laplacian_7pt if kind == "lap7" else gen.laplacian_27pt)(k)
+        order = gen.nested_dissection_order(k)
+    rng = np.random.default_rng(11)
+    dptr, drow, dval = make_dirty(n, ptr, row, val, rng)
+    b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
+    # clean run
+    s0 = sb.Solver()
+    assert s0.analyse(n, ptr, row, order).flag == 0
+    inf0 = s0.factorize(val, posdef=posdef)
+    x0 = s0.solve(b)
+    # dirty run
+    s1 = sb.Solver()
+    i1 = s1.analyse(n, dptr, drow, order, check=True)
+    assert i1.flag == 3 and i1.matrix_outrange > 0 and i1.matrix_dup > 0      # SYLVER_WARNING_DUP_AND_OOR
+    inf1 = s1.factorize(dval, posdef=posdef)
+    assert (inf1.flag >= 0) and (inf1.num_neg, inf1.num_delay) == (inf0.num_neg, inf0.num_delay)
+    x1 = s1.solve(b)
+    assert gen.backward_error(n, ptr, row, val, x1, b) <= 1e-14
+    # generators emit sorted columns, so the cleaned matrix IS the clean matrix
+    c = sb.clean_matrix(n, dptr, drow)
+    assert np.array_equal(c["ptr"], ptr) and np.array_equal(c["row"], row)
+    assert np.array_equal(x1, x0)
+    # a scaling computed at factorize sees the cleaned matrix too
+    s1.options.scaling = 4
+    inf2 = s1.factorize(dval, posdef=posdef)
+    assert inf2.flag >= 0
+    x2 = s1.solve(b)
+    assert gen.backward_error(n, ptr, row, val, x2, b) <= 1e-14
+    s0.free(); s1.free()
