@@ -319,6 +319,12 @@ int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *o
  * offset and count (doubles, inside the front's contribution block), direction (0 send, 1
  * receive).  Returns the number of pieces. */
 int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
+/* Host-only: the level-batched launch plan of the positive definite path for `rank` (fronts that
+ * are not split).  Per level 4 longs (level, fronts, block-column steps of 128, contribution
+ * tiles), then per step 8 longs (fronts that own the block column, panel-solve tiles, trailing
+ * update tiles, of which: first tile column / the rest, first two tile columns / the rest, and
+ * the stride of the inverse slots).  Tiles are 128 x 128.  Returns the number of longs. */
+long sylver_b200_plan_levels(void *akeep, int rank, int world, long cap, long *out);
 
 /* What spldlt_analyse(check = true) does to the matrix, on its own (host only): SPRAL's
  * clean_cscl_oop for a symmetric indefinite matrix (spral/src/matrix_util.f90:1024-1398):

@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale", "sylver_b200_clean_matrix", "sylver_b200_apply_conversion_map",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_plan_levels", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale", "sylver_b200_clean_matrix", "sylver_b200_apply_conversion_map",
 ]
 
 
@@ -157,6 +157,8 @@ def lib() -> C.CDLL:
     L.sylver_b200_partition.argtypes = [vp, C.c_int, vp]
     L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.sylver_b200_plan_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.sylver_b200_plan_levels.argtypes = [vp, C.c_int, C.c_int, C.c_long, vp]
+    L.sylver_b200_plan_levels.restype = C.c_long
     L.sylver_b200_equilib_scale.argtypes = [C.c_int, vp, vp, vp, vp]
     L.sylver_b200_auction_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp]
     L.sylver_b200_hungarian_scale.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]
@@ -326,6 +328,27 @@ def hungarian_scale(n: int, ptr, row, val, scale_if_singular: bool = False):
     if flag == -1:
         raise RuntimeError("sylver_b200_hungarian_scale failed")
     return sc[:n], match[:n], dict(flag=int(inf[0]), matched=int(inf[1]))
+
+
+def plan_levels(solver: "Solver", rank: int = 0, world: int = 1):
+    """Host-only level plan (sylver_b200_plan_levels): list of dicts per level with
+    fronts, contrib_tiles and steps (list of dicts cnt, trsm, upd, updn, updr, upd2n, upd2r, wld)."""
+    cnt = lib().sylver_b200_plan_levels(solver.akeep, rank, world, 0, None)
+    if cnt < 0:
+        raise RuntimeError("sylver_b200_plan_levels failed")
+    buf = np.zeros(max(cnt, 1), dtype=np.int64)
+    lib().sylver_b200_plan_levels(solver.akeep, rank, world, cnt, _ptr(buf))
+    out, k = [], 0
+    keys = ("cnt", "trsm", "upd", "updn", "updr", "upd2n", "upd2r", "wld")
+    while k < cnt:
+        lvl, fronts, nsteps, ctiles = (int(v) for v in buf[k:k + 4])
+        k += 4
+        steps = []
+        for _ in range(nsteps):
+            steps.append(dict(zip(keys, (int(v) for v in buf[k:k + 8]))))
+            k += 8
+        out.append(dict(level=lvl, fronts=fronts, contrib_tiles=ctiles, steps=steps))
+    return out
 
 
 def plan_split(solver: "Solver", rank: int, world: int):

@@ -517,6 +517,12 @@ int sylver_b200_plan_exchanges(void* akeep, int rank, int world, int cap, int* o
    return cnt;
 }
 
+long sylver_b200_plan_levels(void* akeep, int rank, int world, long cap, long* out) {
+   AKeep* ak = static_cast<AKeep*>(akeep);
+   if (!ak || !ak->analysed || !ak->tree || world < 1 || rank < 0 || rank >= world) return -1;
+   return numeric_plan_levels(ak->tree, rank, world, cap, out);
+}
+
 int sylver_b200_equilib_scale(int n, long const* ptr, int const* row, double const* val, double* scaling) {
    if (n < 0 || !ptr || !row || !val || !scaling) return -1;
    return equilib_scale_sym(n, ptr, row, val, scaling);

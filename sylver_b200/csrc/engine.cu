@@ -578,12 +578,14 @@ void posdef_plan_host(NumericTree* nt, bool device) {
    plan_split(nt, device);
 }
 
-static void build_posdef_plan(NumericTree* nt) {
+// Level work lists (tile-count prefix sums, assembly items) on top of posdef_plan_host;
+// device = false keeps everything on the host (sylver_b200_plan_levels, CPU tests).
+static void build_posdef_plan(NumericTree* nt, bool device = true) {
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
    const int nb = nt->nb;
    const int me = nt->rank;
-   posdef_plan_host(nt, true);
+   posdef_plan_host(nt, device);
 
    // work lists
    std::vector<int> prefix;
@@ -751,6 +753,7 @@ static void build_posdef_plan(NumericTree* nt) {
       nt->prof_flops[KC_CONTRIB] += share * n * k * (k + 1);
    }
    nt->W_doubles = wmax;
+   if (!device) return;
    nt->d_prefix = dev_upload(prefix);
    nt->d_asm_work = dev_upload(asmw);
 }
@@ -1302,6 +1305,31 @@ const double* values_on_host(const double* val, size_t count, std::vector<double
       return nullptr;
    }
    return tmp.data();
+}
+
+// Host-only: the level plan of `rank` (batched fronts only; split fronts are planned by
+// plan_split).  Per level one record of 4 longs (level, fronts, block-column steps,
+// contribution tiles) followed by one record of 8 longs per step (fronts, trsm tiles, update
+// tiles, first-tile-column tiles, rest, first-two-tile-columns tiles, rest, inverse stride).
+// Returns the number of longs (may exceed cap).
+long numeric_plan_levels(SymbolicTree* st, int rank, int world, long cap, long* out) {
+   NumericTree nt;
+   nt.st = st;
+   nt.rank = rank;
+   nt.world = world;
+   nt.nb = 128;
+   build_posdef_plan(&nt, false);
+   long k = 0;
+   auto put = [&](long v) { if (k < cap) out[k] = v; ++k; };
+   for (size_t l = 0; l < nt.levels.size(); ++l) {
+      const LevelPlan& lp = nt.levels[l];
+      put((long)l); put(lp.count); put((long)lp.steps.size()); put(lp.contrib_tiles);
+      for (const LevelStep& ls : lp.steps) {
+         put(ls.cnt); put(ls.trsm_tiles); put(ls.upd_tiles); put(ls.updn_tiles); put(ls.updr_tiles);
+         put(ls.upd2n_tiles); put(ls.upd2r_tiles); put(ls.wld);
+      }
+   }
+   return k;
 }
 
 void numeric_tree_split_info(const NumericTree* nt, int* out3) {

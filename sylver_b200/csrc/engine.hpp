@@ -94,6 +94,7 @@ void numeric_tree_timings(const NumericTree* nt, double* out4);
 // contribution pieces this rank sends per factorization
 void numeric_tree_split_info(const NumericTree* nt, int* out3);
 int numeric_plan_split(SymbolicTree* st, int rank, int world, long* out8, int cap, long* pieces);
+long numeric_plan_levels(SymbolicTree* st, int rank, int world, long cap, long* out);
 bool numeric_tree_posdef(const NumericTree* nt);
 // Debug / test access: copy one front's L panel (m x n, ld m) and contribution
 // ((m-n)^2, ld m-n) to host buffers (either may be null). Returns 0 or <0.

@@ -125,3 +125,69 @@ def test_split_can_be_disabled(lib, monkeypatch):
         # without split fronts every cross-rank edge is one whole-block piece
         assert all(off == 0 for (_, _, _, off, _, _) in pieces.tolist())
     s.free()
+
+
+def _ceil(a, b):
+    return -(-a // b)
+
+
+@pytest.mark.parametrize("kind,k,world", [("lap27", 14, 1), ("lap7", 20, 1), ("lap27", 16, 2), ("lap27", 16, 4)])
+def test_level_plan_tile_counts_match_brute_force(lib, monkeypatch, kind, k, world):
+    """The tile-count prefix sums that size every batched launch of the positive definite path
+    (panel solve, trailing update and its look-ahead / paired subsets, contribution update),
+    recomputed from the engine tree by brute force."""
+    monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "200")
+    s, n = analysed(kind, k)
+    et = s.engine_tree()
+    G, nrow, ncol, par = et["nnodes"], et["nrow"], et["ncol"], et["parent"]
+    top = np.zeros(G, dtype=np.int64)
+    top[et["node_map"]] = np.arange(len(et["node_map"]))
+    height = np.zeros(G + 1, dtype=np.int64)
+    for g in range(G):
+        height[par[g]] = max(height[par[g]], height[g] + 1)
+    own = sb.partition(s, world)[top] if world > 1 else np.zeros(G, dtype=np.int64)
+    NB = 128
+    for rank in range(world):
+        levels = sb.plan_levels(s, rank, world)
+        d, _ = sb.plan_split(s, rank, world)
+        nfront = 0
+        for lv in levels:
+            l = lv["level"]
+            mine = [g for g in range(G) if height[g] == l and own[g] == rank]
+            # split fronts are not in the batch; they are few: identify them by the count
+            fronts = sorted(mine, key=lambda g: -ncol[g])
+            assert lv["fronts"] <= len(fronts)
+            if lv["fronts"] < len(fronts):
+                assert world > 1 and d["split_fronts"] > 0
+                continue                       # a level with a split front of this rank: covered by the split tests
+            nfront += len(fronts)
+            maxn = max([ncol[g] for g in fronts], default=0)
+            assert len(lv["steps"]) == _ceil(maxn, NB)
+            ctiles = 0
+            for g in fronts:
+                m_, n_ = int(nrow[g]), int(ncol[g])
+                if m_ > n_:
+                    tr = _ceil(m_ - (n_ & ~1), NB)
+                    ctiles += tr * (tr + 1) // 2
+            assert lv["contrib_tiles"] == ctiles
+            for si, st in enumerate(lv["steps"]):
+                p0 = si * NB
+                act = [g for g in fronts if ncol[g] > p0]
+                assert st["cnt"] == len(act)
+                trsm = upd = updn = upd2n = 0
+                for g in act:
+                    m_, n_ = int(nrow[g]), int(ncol[g])
+                    pw = min(NB, n_ - p0)
+                    if m_ > p0 + pw:
+                        trsm += _ceil(m_ - ((p0 + pw) & ~1), NB)
+                    base = p0 + pw
+                    if n_ > base:
+                        tr, tc = _ceil(m_ - base, NB), _ceil(n_ - base, NB)
+                        upd += sum(tr - tj for tj in range(tc))
+                        updn += tr
+                        upd2n += sum(tr - tj for tj in range(min(tc, 2)))
+                assert (st["trsm"], st["upd"], st["updn"], st["upd2n"]) == (trsm, upd, updn, upd2n)
+                assert st["updn"] + st["updr"] == st["upd"] == st["upd2n"] + st["upd2r"]
+                assert st["wld"] % 4 == 0 and st["wld"] >= min(NB, maxn - p0)
+        assert nfront > 0
+    s.free()
