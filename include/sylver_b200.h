@@ -71,7 +71,9 @@ typedef struct {
                                  (MC64-like); 2: auction matching; >=4: norm equilibration
                                  (MC77-like), all computed at factorize; 3 (scaling saved by a
                                  matching ordering): flag -15, orderings are inputs here */
-   int pivot_method;          /* 1 APP aggressive, 2 APP block, 3 TPP */
+   int pivot_method;          /* 2 APP block (default): a-posteriori pass, then TPP on what failed;
+                                 1 (APP aggressive) and 3 (TPP): TPP on whole fronts, as the
+                                 reference's tree code (serial per front, not for performance) */
    double small;              /* 1e-20 */
    double u;                  /* 0.01 */
    long small_subtree_threshold;

@@ -229,6 +229,11 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    cudaStream_t s = nt->stream;
    const double u = nt->opt.u, small = nt->opt.small;
    const bool tpp_everywhere = (nt->opt.failed_pivot_method != 2) || (nt->opt.pivot_method == 3);
+   // Only pivot_method = 2 (APP block, the default) runs the a-posteriori pass; with 1 (APP
+   // aggressive) and 3 (TPP) the reference's tree code goes straight to threshold partial pivoting
+   // on the whole front (src/factor_indef.hxx:95-139, src/factor_failed.hxx:55-75) -- its serial,
+   // "not for performance" path, and the same one-CTA kernel here.
+   const bool app_block = nt->opt.pivot_method != 1 && nt->opt.pivot_method != 3;
    const bool multi = nt->world > 1;
    const int me = nt->rank;
    int OB = OB_DEFAULT;
@@ -424,7 +429,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          // inside.  After o panels a front has max(0, n - o*OB) active candidates left and inside
          // a panel every block column consumes IB of them (passed or failed), so the launch
          // sequence is known to the host although the outcome of the pivoting is not.
-         const int nouter = (maxn + OB - 1) / OB;
+         const int nouter = app_block ? (maxn + OB - 1) / OB : 0;
          int cnt_o = cnt;
          for (int o = 0; o < nouter; ++o) {
             while (cnt_o > 0 && nt->n[order[cnt_o - 1]] <= o * OB) --cnt_o;
@@ -517,6 +522,11 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    stats->num_zero = hs[3];
    stats->not_first_pass = hs[4];
    stats->not_second_pass = hs[5];
+   if (nt->opt.pivot_method == 3) {
+      // TPP is the first pass then (src/factor_failed.hxx:121-126)
+      stats->not_first_pass = hs[5];
+      stats->not_second_pass = 0;
+   }
    stats->maxfront = maxfront;
    // roots cannot delay: what TPP leaves at a root are exact zero columns (counted above when
    // they were eliminated as zero pivots) -- anything else means a singular matrix and !action
