@@ -101,6 +101,41 @@ def numeric():
     json.dump(out, open(os.path.join(HERE, "numeric.json"), "w"), indent=1)
 
 
+def host_preprocessing():
+    """preprocess.json: outputs of the restatements of SPRAL's Fortran pre-processing
+    (oracle/scaling.py, oracle/matrix_clean.py) on fixed inputs, floats as hex strings: the three
+    scalings (vector, matching, counters) and the cleaned matrix + conversion map.  The product's
+    C++ must reproduce them bit for bit (tests/test_scaling.py, tests/test_matrix_clean.py)."""
+    from oracle import scaling as oscal, matrix_clean as oclean
+    import test_scaling as tsc
+    import test_matrix_clean as tmc
+    out = {"scaling": [], "clean": []}
+    for kind, k, seed in (("lap7", 5, 1), ("kkt", 4, 3)):
+        n, ptr, row, val = tsc.badly_scaled(kind, k, seed)
+        rec = dict(kind=kind, k=k, seed=seed)
+        s, it = oscal.inf_norm_equilib_sym(n, ptr, row, val)
+        rec["equilib"] = dict(scaling=[float(x).hex() for x in s], iterations=int(it))
+        s, m, inf = oscal.auction_scale_sym(n, ptr, row, val)
+        rec["auction"] = dict(scaling=[float(x).hex() for x in s], match=m.tolist(), inform=inf)
+        s, m, inf = oscal.hungarian_scale_sym(n, ptr, row, val)
+        rec["hungarian"] = dict(scaling=[float(x).hex() for x in s], match=m.tolist(), inform=inf)
+        out["scaling"].append(rec)
+    for seed in (501, 507):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(10, 40))
+        ptr, row, val = tmc.dirty_random(n, rng)
+        c = oclean.clean_cscl_oop_sym_indef(n, ptr, row)
+        out["clean"].append(dict(seed=seed, n=n, ptr_in=ptr.tolist(), row_in=row.tolist(),
+                                 val_in=[float(x).hex() for x in val], flag=c["flag"], noor=c["noor"], ndup=c["ndup"],
+                                 ptr=c["ptr"].tolist(), row=c["row"].tolist(), map=c["map"].tolist(),
+                                 val=[float(x).hex() for x in oclean.apply_conversion_map(c, val)]))
+    json.dump(out, open(os.path.join(HERE, "preprocess.json"), "w"))
+
+
 if __name__ == "__main__":
-    symbolic()
-    numeric()
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        host_preprocessing()
+    else:
+        symbolic()
+        numeric()
+        host_preprocessing()

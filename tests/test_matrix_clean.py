@@ -145,3 +145,20 @@ def test_checked_analysis_equals_analysis_of_the_clean_matrix(lib):
         assert np.array_equal(y1[key], y2[key]), key
     assert (i1.num_factor, i1.num_flops) == (i2.num_factor, i2.num_flops)
     s1.free(); s2.free()
+
+
+def test_committed_golden_vectors(lib):
+    """tests/golden/preprocess.json: cleaned structure, conversion map and mapped values of
+    fixed dirty matrices, as the oracle restatement produced them."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "preprocess.json")))
+    assert len(g["clean"]) >= 2
+    for rec in g["clean"]:
+        ptr = np.array(rec["ptr_in"], dtype=np.int64)
+        row = np.array(rec["row_in"], dtype=np.int32)
+        val = np.array([float.fromhex(x) for x in rec["val_in"]])
+        c = sb.clean_matrix(rec["n"], ptr, row)
+        assert (c["flag"], c["noor"], c["ndup"]) == (rec["flag"], rec["noor"], rec["ndup"])
+        assert c["ptr"].tolist() == rec["ptr"] and c["row"].tolist() == rec["row"] and c["map"].tolist() == rec["map"]
+        assert [float(x).hex() for x in sb.apply_conversion_map(c, val)] == rec["val"]
