@@ -206,36 +206,3 @@ def test_singular_matrix_warning(lib):
     s2.options.action = False
     s2.analyse(3, ptr, row, np.arange(1, 4, dtype=np.int32))
     assert s2.factorize(val, posdef=False).flag == -5
-
-
-@pytest.mark.parametrize("pivot_method", [1, 3])
-@pytest.mark.parametrize("kind,k", [("lap7", 8), ("kkt", 5)])
-def test_tpp_only_pivot_methods(lib, oracle_ref, kind, k, pivot_method):
-    """options.pivot_method = 1 (APP aggressive) and 3 (TPP): like the reference's tree code the
-    engine skips the a-posteriori pass and eliminates every front by threshold partial pivoting
-    (src/factor_indef.hxx:95-139, src/factor_failed.hxx:55-75).  Same inertia and backward-error
-    bar as the default method; the oracle runs with the same option."""
-    sb.require_gpu()
-    if kind == "kkt":
-        n, ptr, row, val = gen.stokes_kkt(k)
-        order = gen.nested_dissection_order(k, dofs_per_cell=4)
-    else:
-        n, ptr, row, val = gen.laplacian_7pt(k)
-        order = gen.nested_dissection_order(k)
-    b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
-    s = sb.Solver()
-    assert s.analyse(n, ptr, row, order).flag == 0
-    s.options.pivot_method = pivot_method
-    inf = s.factorize(val, posdef=False)
-    assert inf.flag >= 0, inf.flag
-    x = s.solve(b)
-    be = gen.backward_error(n, ptr, row, val, x, b)
-    opt = oracle_ref.default_options()
-    opt.pivot_method = pivot_method
-    ot = oracle_ref.OracleTree(s.symbolic(), opt)
-    ot.factor(val, False)
-    xo = ot.solve_original(b)
-    beo = gen.backward_error(n, ptr, row, val, xo, b)
-    assert inf.num_neg == ot.stats.num_neg
-    assert be <= 1e-14 and be <= 10 * max(beo, 2e-16), (be, beo)
-    s.free(); ot.close()

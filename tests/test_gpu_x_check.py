@@ -1,4 +1,5 @@
-"""spldlt_analyse(check=True) end to end on the GPU: a Laplacian / KKT matrix made dirty
+"""[First GPU run is the driver's: written after this round's GPU budget was spent; the file
+name sorts after the validated suites.]  spldlt_analyse(check=True) end to end on the GPU: a Laplacian / KKT matrix made dirty
 (duplicates that sum to the original entries exactly, entries above the diagonal, rows outside
 1..n, shuffled columns) must be factorized and solved exactly like the clean matrix -- the
 cleaned structure is the clean matrix and the conversion map reproduces its values bit for bit."""

@@ -1,4 +1,5 @@
-"""Random sparse symmetric indefinite matrices of the reference lineage's test family
+"""[First GPU run is the driver's: written after this round's GPU budget was spent; the file
+name sorts after the validated suites.]  Random sparse symmetric indefinite matrices of the reference lineage's test family
 (SPRAL's random_matrix_generate + gen_random_sym: forced diagonal, some zero diagonal entries,
 off-diagonals scaled by 1000 -- restated in oracle/spral_random.py) through analyse / factorize /
 solve.  Natural order, so the trees are irregular and the LDL^T delays many pivots.  These

@@ -1,4 +1,5 @@
-"""Scaled factorizations on the GPU: options.scaling >= 4 (norm
+"""[First GPU run is the driver's: written after this round's GPU budget was spent; the file
+name sorts after the validated suites.]  Scaled factorizations on the GPU: options.scaling >= 4 (norm
 equilibration), == 2 (auction matching) and == 1 (Hungarian matching), all computed at factorize,
 and a user-supplied scaling.  The matrices are Laplacian /
 KKT systems with rows and columns scaled by 10^U(-4,4): the scaled backward error of the solve
