@@ -83,3 +83,24 @@ def test_version_and_device_count_do_not_need_a_gpu(lib):
 def test_product_does_not_link_the_oracle():
     out = subprocess.run(["ldd", sb.LIB_PATH], capture_output=True, text=True).stdout
     assert "liboracle" not in out and "openblas" not in out
+
+
+def _build_example(tmpdir):
+    exe = os.path.join(tmpdir, "example")
+    libdir = os.path.join(ROOT, "sylver_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "spldlt_simple_example.c"), "-L", libdir, "-lsylver_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    return exe
+
+
+def test_c_example_compiles_and_links(lib):
+    """The reference's C example, with a supplied order, builds against the header and the
+    library with a plain C compiler (no C++, no CUDA headers needed by the caller)."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d)
+        assert os.path.exists(exe)
+        if sb.device_count() == 0:
+            # without a device the program must fail loudly at factorize, not fall back
+            r = subprocess.run([exe], capture_output=True, text=True)
+            assert r.returncode == 1 and "factorize failed: -51" in r.stdout

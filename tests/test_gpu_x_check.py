@@ -70,3 +70,19 @@ def test_checked_matrix_is_factorized_like_the_clean_one(lib, kind, k, posdef):
     x2 = s1.solve(b)
     assert gen.backward_error(n, ptr, row, val, x2, b) <= 1e-14
     s0.free(); s1.free()
+
+
+def test_c_example_known_answer(lib):
+    """examples/spldlt_simple_example.c (the reference's C example with a supplied order, checked
+    analyse, LDL^T) built with gcc and run: x = (1.5, 2, 1.5), no negative pivots."""
+    import os
+    import subprocess
+    import tempfile
+    from test_abi import _build_example
+    sb.require_gpu()
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([_build_example(d)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vals = r.stdout.split("=")[1].split("(")[0].split()
+    assert np.allclose([float(v) for v in vals], [1.5, 2.0, 1.5], rtol=1e-14)
+    assert "num_neg 0" in r.stdout
