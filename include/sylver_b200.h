@@ -63,7 +63,10 @@ typedef struct {
    int unit_diagnostics;
    int unit_error;
    int unit_warning;
-   int ordering;              /* 0 = user order (the only one implemented here) */
+   int ordering;              /* 0 = user order; 1 = METIS nested dissection (the reference's
+                                 default; through the METIS 5 static library of the CUDA toolkit
+                                 when the library was built with it, else flag -98); 2 (matching
+                                 based): flag -98 */
    int nemin;                 /* 32 */
    bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
    long min_gpu_work;
@@ -119,8 +122,9 @@ void sylver_init(int ncpu, int ngpu);
 void sylver_finalize(void);
 /* sylver.h:77 */
 void sylver_default_options(sylver_options_t *options);
-/* sylver.h:79-83 ; options->ordering must be 0 (order supplied), order is
- * overwritten with the final elimination order.  check = true: the matrix is cleaned first
+/* sylver.h:79-83 ; options->ordering 0: order supplied (order[i] = 1-based position of variable
+ * i+1); 1: computed by METIS, order may be NULL.  order (if given) is overwritten with the
+ * final elimination order.  check = true: the matrix is cleaned first
  * (out-of-range entries dropped, duplicates summed: inform->matrix_outrange / matrix_dup, warning
  * flags 1..5, errors -3 / -4 as the reference); spldlt_factorize then maps the caller's val
  * through the saved conversion map.  check = false: the matrix must be a clean lower triangle. */
@@ -320,6 +324,11 @@ int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *o
  * receives 6 longs per piece while they fit in cap: level, front (topmost reference node), peer,
  * offset and count (doubles, inside the front's contribution block), direction (0 send, 1
  * receive).  Returns the number of pieces. */
+/* The ordering of options->ordering == 1 on its own (host only): METIS_NodeND with default
+ * options on the adjacency lists SPRAL's metis_order builds (spral/src/metis5_wrapper.f90).
+ * order[i] = 1-based position of variable i+1, invp its inverse.  Returns 0, -1 (allocation),
+ * -2 (built without METIS) or -99. */
+int sylver_b200_metis_order(int n, long const *ptr, int const *row, int *order, int *invp);
 int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
 /* Host-only: the level-batched launch plan of the positive definite path for `rank` (fronts that
  * are not split).  Per level 4 longs (level, fronts, block-column steps of 128, contribution

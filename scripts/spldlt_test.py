@@ -2,12 +2,12 @@
 Rutherford-Boeing matrix, b = A * 1, analyse, factorize, solve, report times and errors.
 
   python scripts/spldlt_test.py --mat matrix.rb [--posdef | --indef] [--nrhs 1] [--nemin 32]
-        [--scale=none|mc64|auction|mc77] [--order=rcm|natural|FILE] [--check] [--u 0.01]
+        [--scale=none|mc64|auction|mc77] [--order=metis|rcm|natural|FILE] [--check] [--u 0.01]
         [--failed-pivot-method=tpp|pass] [--ngpu 1]
 
-Differences from the Fortran driver, all forced by the scope: the ordering is an
-input of this library (METIS is not vendored), so --order picks reverse Cuthill-McKee (scipy),
-the natural order, or a file with one 1-based position per line; --ncpu, --nb, --prune-tree,
+Like the Fortran driver the default ordering is METIS (options.ordering = 1, through the static
+METIS of the CUDA toolkit); --order can also pick reverse Cuthill-McKee (scipy), the natural
+order, or a file with one 1-based position per line.  --ncpu, --nb, --prune-tree,
 --sched=*, --*-topology and --gpu-perf-coeff are accepted and ignored (every front runs on the GPU).
 """
 import argparse
@@ -23,6 +23,8 @@ from sylver_b200 import gen, rb
 
 
 def pick_order(spec, n, ptr, row):
+    if spec == "metis":
+        return None                      # options.ordering = 1: computed by analyse
     if spec == "natural":
         return np.arange(1, n + 1, dtype=np.int32)
     if spec == "rcm":
@@ -46,7 +48,7 @@ def main(argv=None):
     ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--nemin", type=int, default=32)
     ap.add_argument("--scale", default="none", choices=["none", "mc64", "auction", "mc77"])
-    ap.add_argument("--order", default="rcm")
+    ap.add_argument("--order", default="metis")
     ap.add_argument("--check", action="store_true", help="analyse with check=true (matrix cleaning)")
     ap.add_argument("--u", type=float, default=0.01)
     ap.add_argument("--failed-pivot-method", default="tpp", choices=["tpp", "pass"])
@@ -74,6 +76,13 @@ def main(argv=None):
     s.options.scaling = {"none": 0, "mc64": 1, "auction": 2, "mc77": 4}[a.scale]
     s.options.failed_pivot_method = 1 if a.failed_pivot_method == "tpp" else 2
     order = pick_order(a.order, n, ptr, row)
+    if order is None:
+        if sb.metis_order(3, np.array([1, 2, 3, 4]), np.array([1, 2, 3], dtype=np.int32)) is None:
+            raise SystemExit("this build has no METIS: pass --order=rcm|natural|FILE")
+        s.options.ordering = 1
+        order = np.zeros(n, dtype=np.int32)
+    else:
+        s.options.ordering = 0
 
     t = time.perf_counter()
     inf = s.analyse(n, ptr, row, order, val=val, check=a.check)

@@ -16,11 +16,16 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsylver_b200.so")
 
-SOURCES = ["api.cpp", "analyse.cpp", "scaling.cpp", "clean.cpp", "partition.cpp", "comm.cpp", "engine.cu", "engine_indef.cu", "aux.cu"]
+SOURCES = ["api.cpp", "analyse.cpp", "scaling.cpp", "clean.cpp", "ordering.cpp", "partition.cpp", "comm.cpp", "engine.cu", "engine_indef.cu", "aux.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# METIS 5 (idx_t = int64) ships with the CUDA toolkit as a static library; options.ordering = 1
+# is available when it is found (csrc/ordering.cpp), otherwise that option returns flag -98
+METIS_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(NVCC))), "targets", "x86_64-linux", "lib",
+                         "libmetis_static.a")
+HAVE_METIS = os.path.exists(METIS_LIB)
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-          "-Xptxas", "-v" if os.environ.get("SYLVER_PTXAS_V") else "-O3"]
+          "-Xptxas", "-v" if os.environ.get("SYLVER_PTXAS_V") else "-O3"] + (["-DSYLVER_HAVE_METIS"] if HAVE_METIS else [])
 
 
 def _deps(src: str):
@@ -60,7 +65,8 @@ def build(force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(_compile, srcs))
     if _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, *([METIS_LIB] if HAVE_METIS else []),
+               "-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))

@@ -15,6 +15,7 @@
 #include "comm.hpp"
 #include "clean.hpp"
 #include "engine.hpp"
+#include "ordering.hpp"
 #include "scaling.hpp"
 
 using namespace sylver_b200;
@@ -138,13 +139,14 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
    if (n < 0) { inform->flag = SYLVER_ERROR_A_N_OOR; ak->inform = *inform; return; }
    if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; ak->inform = *inform; return; }
    if (options->ordering < 0 || options->ordering > 2) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
-   if (options->ordering != 0) {
-      // METIS / matching orderings are un-vendored pre-processing: order is an input here
+   if (options->ordering == 2 || (options->ordering == 1 && !metis_available())) {
+      // matching-based ordering (2: MC64 + METIS on the compressed graph) is not built; METIS (1)
+      // needs the static library of the CUDA toolkit at build time (csrc/ordering.cpp)
       inform->flag = (options->ordering == 2 && !val) ? SYLVER_ERROR_VAL : SYLVER_ERROR_UNIMPLEMENTED;
       ak->inform = *inform;
       return;
    }
-   if (n > 0 && !order) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
+   if (options->ordering == 0 && n > 0 && !order) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
    if (check) {
       // out-of-range entries dropped, duplicates summed, rows sorted; warnings keep matrix_util's
       // numbering (src/spldlt_analyse_mod.F90:707-739)
@@ -161,6 +163,21 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       row = ak->clean.row.data();
    }
    const int clean_flag = check ? ak->clean.flag : 0;
+   std::vector<int> metis_perm;
+   int* user_order = order;
+   if (options->ordering == 1 && n > 0) {
+      // METIS nested dissection on the (cleaned) pattern (src/spldlt_analyse_mod.F90:748-757 ->
+      // spral metis_order); the order goes back to the caller if an array was passed
+      metis_perm.resize(n);
+      std::vector<int> invp(n);
+      const int mf = metis_order(n, ptr, row, metis_perm.data(), invp.data());
+      if (mf != 0) {
+         inform->flag = mf == -1 ? SYLVER_ERROR_ALLOCATION : SYLVER_ERROR_UNKNOWN;
+         ak->inform = *inform;
+         return;
+      }
+      order = metis_perm.data();
+   }
    int flag;
    try {
       flag = analyse(n, ptr, row, order, options->nemin, ak->sym);
@@ -175,7 +192,8 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       ak->tree = symbolic_tree_create(n, s.nnodes, s.sptr.data(), s.sparent.data(), s.rptr.data(), s.rlist.data(),
                                       s.nptr.data(), s.nlist.data(), &tflag);
       if (!ak->tree) { inform->flag = tflag ? tflag : SYLVER_ERROR_UNKNOWN; ak->inform = *inform; return; }
-      for (int i = 0; i < n; ++i) order[i] = std::abs(s.order[i]);
+      if (user_order)
+         for (int i = 0; i < n; ++i) user_order[i] = std::abs(s.order[i]);
    }
    inform->num_factor = s.num_factor;
    inform->num_flops = s.num_flops;
@@ -568,6 +586,12 @@ int sylver_b200_hungarian_scale(int n, long const* ptr, int const* row, double c
    const int flag = hungarian_scale_sym(n, ptr, row, val, scaling, match, scale_if_singular != 0, &inf);
    if (inform2) { inform2[0] = inf.flag; inform2[1] = inf.matched; }
    return flag;
+}
+
+int sylver_b200_metis_order(int n, long const* ptr, int const* row, int* order, int* invp) {
+   if (n < 0 || !ptr || !row || !order || !invp) return -99;
+   if (n == 0) return 0;
+   return metis_order(n, ptr, row, order, invp);
 }
 
 int sylver_b200_plan_split(void* akeep, int rank, int world, long* out8, int cap, long* pieces) {

@@ -1,0 +1,17 @@
+// options.ordering = 1: fill-reducing ordering by METIS nested dissection, as the reference
+// computes it (spral/src/metis5_wrapper.f90:110-166 metis_order -> METIS_NodeND with default
+// options), through the METIS 5 static library that ships with the CUDA toolkit
+// (targets/x86_64-linux/lib/libmetis_static.a, idx_t = int64).  Host code.
+#pragma once
+
+namespace sylver_b200 {
+
+// true when the library was built with METIS
+bool metis_available();
+
+// Lower triangle CSC, 1-based ptr/row (diagonal entries allowed, no duplicates).
+// perm[i] = position (1-based) of variable i+1 in the elimination order; invp = its inverse.
+// Returns 0, -1 allocation failure, -2 METIS not available, -99 METIS error.
+int metis_order(int n, const long* ptr, const int* row, int* perm, int* invp);
+
+}  // namespace sylver_b200
