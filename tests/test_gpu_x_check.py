@@ -86,3 +86,35 @@ def test_c_example_known_answer(lib):
     vals = r.stdout.split("=")[1].split("(")[0].split()
     assert np.allclose([float(v) for v in vals], [1.5, 2.0, 1.5], rtol=1e-14)
     assert "num_neg 0" in r.stdout
+
+
+@pytest.mark.parametrize("kind,k,posdef", [("lap7", 12, True), ("lap27", 9, True), ("lap7", 12, False), ("kkt", 8, False)])
+def test_metis_ordered_factorization(lib, oracle_ref, kind, k, posdef):
+    """options.ordering = 1 end to end: METIS's nested dissection gives irregular trees (unlike
+    the geometric orders of the other suites).  Same bar: oracle inertia on the same tree,
+    backward error <= 1e-14 and within 10x of the oracle."""
+    sb.require_gpu()
+    if kind == "kkt":
+        n, ptr, row, val = gen.stokes_kkt(k)
+    else:
+        n, ptr, row, val = (gen.laplacian_7pt if kind == "lap7" else gen.laplacian_27pt)(k)
+    if sb.metis_order(n, ptr, row) is None:
+        pytest.skip("library built without METIS")
+    b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
+    s = sb.Solver()
+    s.options.ordering = 1
+    order = np.zeros(n, dtype=np.int32)
+    assert s.analyse(n, ptr, row, order, check=True).flag == 0
+    assert np.array_equal(np.sort(s.order), np.arange(1, n + 1))          # the order METIS chose comes back
+    inf = s.factorize(val, posdef=posdef)
+    assert inf.flag >= 0, inf.flag
+    x = s.solve(b)
+    be = gen.backward_error(n, ptr, row, val, x, b)
+    ot = oracle_ref.OracleTree(s.symbolic())
+    ot.factor(val, posdef)
+    xo = ot.solve_original(b)
+    beo = gen.backward_error(n, ptr, row, val, xo, b)
+    if not posdef:
+        assert inf.num_neg == ot.stats.num_neg
+    assert be <= 1e-14 and be <= 10 * max(beo, 2e-16), (be, beo)
+    s.free(); ot.close()
