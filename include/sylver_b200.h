@@ -64,16 +64,18 @@ typedef struct {
    int unit_error;
    int unit_warning;
    int ordering;              /* 0 = user order; 1 = METIS nested dissection (the reference's
-                                 default; through the METIS 5 static library of the CUDA toolkit
-                                 when the library was built with it, else flag -98); 2 (matching
-                                 based): flag -98 */
+                                 default); 2 = matching-based ordering (Hungarian matching,
+                                 matched pairs kept adjacent, METIS on the compressed graph;
+                                 needs val; its scaling is reused by scaling = 3).  1 and 2 go
+                                 through the METIS 5 static library of the CUDA toolkit when the
+                                 library was built with it, else flag -98 */
    int nemin;                 /* 32 */
    bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
    long min_gpu_work;
    int scaling;               /* <=0: none / user supplied in `scale`; 1: Hungarian matching
                                  (MC64-like); 2: auction matching; >=4: norm equilibration
-                                 (MC77-like), all computed at factorize; 3 (scaling saved by a
-                                 matching ordering): flag -15, orderings are inputs here */
+                                 (MC77-like), all computed at factorize; 3: the scaling saved by
+                                 analyse with ordering = 2 (flag -15 if there is none) */
    int pivot_method;          /* 2 APP block (default): a-posteriori pass, then TPP on what failed;
                                  1 (APP aggressive) and 3 (TPP): TPP on whole fronts, as the
                                  reference's tree code (serial per front, not for performance) */
@@ -112,7 +114,8 @@ enum {
    SYLVER_ERROR_UNIMPLEMENTED = -98,
    SYLVER_ERROR_UNKNOWN = -99,
    SYLVER_WARNING_ANAL_SINGULAR = 6,
-   SYLVER_WARNING_FACT_SINGULAR = 7
+   SYLVER_WARNING_FACT_SINGULAR = 7,
+   SYLVER_WARNING_MATCH_ORD_NO_SCALE = 8
 };
 
 /* sylver.h:73  -- ncpu is accepted and ignored; ngpu = number of B200s this
@@ -329,6 +332,13 @@ int sylver_b200_plan_exchanges(void *akeep, int rank, int world, int cap, int *o
  * order[i] = 1-based position of variable i+1, invp its inverse.  Returns 0, -1 (allocation),
  * -2 (built without METIS) or -99. */
 int sylver_b200_metis_order(int n, long const *ptr, int const *row, int *order, int *invp);
+/* The ordering of options->ordering == 2 on its own (host only): SPRAL match_order_metis
+ * (spral/src/match_order.f90:135-629).  order[i] = 1-based position of variable i+1; scale = the
+ * symmetric matching scaling (what options->scaling == 3 applies); pairs (n ints, may be NULL):
+ * the 1-based partner of every variable in a 2x2 pivot, -1 for a 1x1 pivot, -2 for an unmatched
+ * variable.  Returns 0, 1 (structurally singular), -1, -2 (built without METIS) or -99. */
+int sylver_b200_match_order(int n, long const *ptr, int const *row, double const *val, int *order, double *scale,
+                            int *pairs);
 int sylver_b200_plan_split(void *akeep, int rank, int world, long *out8, int cap, long *pieces);
 /* Host-only: the level-batched launch plan of the positive definite path for `rank` (fronts that
  * are not split).  Per level 4 longs (level, fronts, block-column steps of 128, contribution

@@ -84,7 +84,7 @@ EXPORTS = [
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
     "sylver_b200_comm_init_local",
-    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_plan_levels", "sylver_b200_metis_order", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale", "sylver_b200_clean_matrix", "sylver_b200_apply_conversion_map",
+    "sylver_b200_partition", "sylver_b200_plan_exchanges", "sylver_b200_plan_split", "sylver_b200_plan_levels", "sylver_b200_metis_order", "sylver_b200_match_order", "sylver_b200_equilib_scale", "sylver_b200_auction_scale", "sylver_b200_hungarian_scale", "sylver_b200_clean_matrix", "sylver_b200_apply_conversion_map",
 ]
 
 
@@ -158,6 +158,7 @@ def lib() -> C.CDLL:
     L.sylver_b200_plan_exchanges.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.sylver_b200_plan_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.sylver_b200_metis_order.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.sylver_b200_match_order.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp]
     L.sylver_b200_plan_levels.argtypes = [vp, C.c_int, C.c_int, C.c_long, vp]
     L.sylver_b200_plan_levels.restype = C.c_long
     L.sylver_b200_equilib_scale.argtypes = [C.c_int, vp, vp, vp, vp]
@@ -344,6 +345,23 @@ def metis_order(n: int, ptr, row):
     if rc != 0:
         raise RuntimeError(f"sylver_b200_metis_order failed ({rc})")
     return order[:n], invp[:n]
+
+
+def match_order(n: int, ptr, row, val):
+    """Matching-based ordering (sylver_b200_match_order): (flag, order, scale, pairs); None if
+    the library was built without METIS."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    row = np.ascontiguousarray(row, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    scale = np.zeros(max(n, 1))
+    pairs = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib().sylver_b200_match_order(n, _ptr(ptr), _ptr(row), _ptr(val), _ptr(order), _ptr(scale), _ptr(pairs))
+    if rc == -2:
+        return None
+    if rc < 0:
+        raise RuntimeError(f"sylver_b200_match_order failed ({rc})")
+    return rc, order[:n], scale[:n], pairs[:n]
 
 
 def plan_levels(solver: "Solver", rank: int = 0, world: int = 1):

@@ -33,6 +33,7 @@ struct AKeep {
    bool analysed = false;
    bool check = false;        // analyse(check = true): the matrix below replaces the caller's
    CleanMatrix clean;         // cleaned structure + conversion map (akeep%ptr/row/map/lmap)
+   std::vector<double> match_scaling;   // options.ordering = 2: scaling saved for options.scaling = 3
 };
 
 struct FKeep {
@@ -134,15 +135,17 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       ak->sym = Symbolic();
       ak->analysed = false;
       ak->clean = CleanMatrix();
+      ak->match_scaling.clear();
    }
    ak->check = check;
    if (n < 0) { inform->flag = SYLVER_ERROR_A_N_OOR; ak->inform = *inform; return; }
    if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; ak->inform = *inform; return; }
    if (options->ordering < 0 || options->ordering > 2) { inform->flag = SYLVER_ERROR_ORDER; ak->inform = *inform; return; }
-   if (options->ordering == 2 || (options->ordering == 1 && !metis_available())) {
-      // matching-based ordering (2: MC64 + METIS on the compressed graph) is not built; METIS (1)
-      // needs the static library of the CUDA toolkit at build time (csrc/ordering.cpp)
-      inform->flag = (options->ordering == 2 && !val) ? SYLVER_ERROR_VAL : SYLVER_ERROR_UNIMPLEMENTED;
+   if (options->ordering == 2 && !val) { inform->flag = SYLVER_ERROR_VAL; ak->inform = *inform; return; }
+   if (options->ordering != 0 && !metis_available()) {
+      // METIS (1) and the matching-based ordering (2) need the static METIS of the CUDA toolkit
+      // at build time (csrc/ordering.cpp)
+      inform->flag = SYLVER_ERROR_UNIMPLEMENTED;
       ak->inform = *inform;
       return;
    }
@@ -178,6 +181,33 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       }
       order = metis_perm.data();
    }
+   int match_flag = 0;
+   if (options->ordering == 2 && n > 0) {
+      // matching-based ordering on the (cleaned) matrix; its scaling is kept for
+      // options.scaling = 3 (src/spldlt_analyse_mod.F90:788-817)
+      std::vector<double> vtmp, vclean;
+      long nin = ptr[n] - 1;
+      if (check) {
+         nin = 0;
+         for (long i = 0; i < ak->clean.lmap; ++i) nin = std::max(nin, ak->clean.map[i]);
+      }
+      const double* hval = values_on_host(val, (size_t)nin, vtmp);
+      if (!hval) { inform->flag = SYLVER_ERROR_CUDA_UNKNOWN; ak->inform = *inform; return; }
+      if (check) {
+         vclean.resize(ak->clean.row.size() + 1);
+         apply_conversion_map(ak->clean, hval, vclean.data());
+         hval = vclean.data();
+      }
+      metis_perm.resize(n);
+      ak->match_scaling.assign(n, 1.0);
+      match_flag = match_order_metis(n, ptr, row, hval, metis_perm.data(), ak->match_scaling.data(), nullptr);
+      if (match_flag < 0) {
+         inform->flag = match_flag == -1 ? SYLVER_ERROR_ALLOCATION : SYLVER_ERROR_UNKNOWN;
+         ak->inform = *inform;
+         return;
+      }
+      order = metis_perm.data();
+   }
    int flag;
    try {
       flag = analyse(n, ptr, row, order, options->nemin, ak->sym);
@@ -185,7 +215,7 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       flag = ANAL_ERROR_ALLOCATION;
    }
    if (flag < 0) { inform->flag = flag; ak->inform = *inform; return; }
-   inform->flag = flag > 0 ? flag : clean_flag;      // the singularity warning replaces a cleaning warning (:805-810)
+   inform->flag = (flag > 0 || match_flag == 1) ? ANAL_WARNING_ANAL_SINGULAR : clean_flag;      // the singularity warning replaces a cleaning warning (:805-810)
    Symbolic& s = ak->sym;
    if (n > 0) {
       int tflag = 0;
@@ -240,17 +270,20 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
       ptr = ak->clean.ptr.data();
       row = ak->clean.row.data();
    }
-   if (options->scaling == 3) {
-      // the scaling saved by a matching-based ORDERING at analyse: orderings are inputs here
-      // (options.ordering must be 0), so there is never a saved scaling
-      // (spldlt_factorize_mod.F90:797-802)
+   if (options->scaling == 3 && ak->match_scaling.empty()) {
+      // no scaling saved by a matching-based ordering at analyse (spldlt_factorize_mod.F90:797-802)
       inform->flag = SYLVER_ERROR_NO_SAVED_SCALING;
       fk->inform = *inform;
       return;
    }
+   // a scaling was computed with the matching-based ordering and is being ignored (:720-724)
+   if (!ak->match_scaling.empty() && options->scaling != 3) inform->flag = SYLVER_WARNING_MATCH_ORD_NO_SCALE;
    const bool had_scaling = !fk->scaling.empty();
    fk->scaling.clear();
-   if (options->scaling > 0) {
+   if (options->scaling == 3) {
+      fk->scaling.resize(n);
+      for (int i = 0; i < n; ++i) fk->scaling[i] = ak->match_scaling[ak->sym.invp[i] - 1];
+   } else if (options->scaling > 0) {
       // computed here: Hungarian matching (1, spldlt_factorize_mod.F90:738-769), auction matching
       // (2, :771-795) or norm equilibration (>= 4, :804-831); permuted to elimination order,
       // handed back in `scale`
@@ -586,6 +619,12 @@ int sylver_b200_hungarian_scale(int n, long const* ptr, int const* row, double c
    const int flag = hungarian_scale_sym(n, ptr, row, val, scaling, match, scale_if_singular != 0, &inf);
    if (inform2) { inform2[0] = inf.flag; inform2[1] = inf.matched; }
    return flag;
+}
+
+int sylver_b200_match_order(int n, long const* ptr, int const* row, double const* val, int* order, double* scale,
+                            int* pairs) {
+   if (n < 0 || !ptr || !row || !val || !order || !scale) return -99;
+   return match_order_metis(n, ptr, row, val, order, scale, pairs);
 }
 
 int sylver_b200_metis_order(int n, long const* ptr, int const* row, int* order, int* invp) {

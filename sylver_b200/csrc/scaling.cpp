@@ -318,6 +318,8 @@ void hungarian_init_heuristic(int m, int n, const std::vector<long>& ptr, const 
    }
 }
 
+}  // namespace
+
 // scaling.f90:938-1194.  iperm(i) = column matched to row i (negative completion when singular)
 void hungarian_match(int m, int n, const std::vector<long>& ptr, const std::vector<int>& row,
                      const std::vector<double>& val, std::vector<int>& iperm, int& num, std::vector<double>& dualu,
@@ -492,6 +494,8 @@ void hungarian_match(int m, int n, const std::vector<long>& ptr, const std::vect
       iperm[jdum] = -j;
    }
 }
+
+namespace {
 
 // match_postproc for a square matrix (scaling.f90:1631-1638)
 void match_postproc_square(int n, std::vector<double>& rscaling, std::vector<double>& cscaling) {

@@ -2,6 +2,7 @@
 // (spral/src/scaling.f90), which the reference calls from spldlt_factorize
 // (src/spldlt_factorize_mod.F90:727-835).
 #pragma once
+#include <vector>
 
 namespace sylver_b200 {
 
@@ -34,5 +35,13 @@ struct HungarianInform {
 // singular matrix the unmatched rows hold negative values as in the reference.
 int hungarian_scale_sym(int n, const long* ptr, const int* row, const double* val, double* scaling, int* match,
                         bool scale_if_singular, HungarianInform* inform);
+
+// The core assignment solver (scaling.f90:938-1194), all arrays 1-based with a dummy element 0:
+// minimum-sum matching of the m x n matrix (ptr, row, val >= 0); iperm[i] = column matched to row
+// i (negative values complete the matching of a structurally singular matrix), num = cardinality,
+// dualu / dualv the dual variables.  Shared with the matching-based ordering (ordering.cpp).
+void hungarian_match(int m, int n, const std::vector<long>& ptr, const std::vector<int>& row,
+                     const std::vector<double>& val, std::vector<int>& iperm, int& num, std::vector<double>& dualu,
+                     std::vector<double>& dualv);
 
 }  // namespace sylver_b200

@@ -51,7 +51,8 @@ def test_analyse_argument_errors(lib):
     assert raw_analyse(o.ctypes.data_as(C.c_void_p), ordering=1) == (SUCCESS if sb.metis_order(n, ptr, row) else UNIMPLEMENTED)
     assert raw_analyse(None, ordering=1) == (SUCCESS if sb.metis_order(n, ptr, row) else UNIMPLEMENTED)   # order may be absent
     val_p = val.ctypes.data_as(C.c_void_p)
-    assert raw_analyse(o.ctypes.data_as(C.c_void_p), ordering=2, val_ptr=val_p) == UNIMPLEMENTED   # matching-based: not built
+    assert raw_analyse(o.ctypes.data_as(C.c_void_p), ordering=2, val_ptr=val_p) == (
+        SUCCESS if sb.metis_order(n, ptr, row) else UNIMPLEMENTED)       # matching-based ordering needs METIS too
     assert raw_analyse(o.ctypes.data_as(C.c_void_p), n_=-1) == A_N_OOR
     # factorize after a failed analyse: call sequence error
     assert s.factorize(val, posdef=True).flag == CALL_SEQUENCE

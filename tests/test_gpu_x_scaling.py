@@ -66,3 +66,37 @@ def test_scaled_factorization(lib, oracle_ref, kind, k, posdef, mode):
     beo = gen.backward_error(n, ptr, row, val, y, b)
     assert be <= 10 * max(beo, 2e-16), (be, beo)
     s.free(); s2.free(); ot.close()
+
+
+@pytest.mark.parametrize("kind,k", [("kkt", 8), ("lap7", 12)])
+def test_matching_based_ordering_with_saved_scaling(lib, oracle_ref, kind, k):
+    """options.ordering = 2 (Hungarian matching + METIS on the compressed graph) followed by
+    options.scaling = 3 (the scaling that analyse saved) -- the reference's recipe for hard
+    indefinite systems; scaling = 0 afterwards raises the "matching ordering, no scaling"
+    warning (8) and still factorizes."""
+    sb.require_gpu()
+    n, ptr, row, val = badly_scaled(kind, k, 5)
+    if sb.match_order(n, ptr, row, val) is None:
+        pytest.skip("library built without METIS")
+    b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
+    s = sb.Solver()
+    s.options.ordering = 2
+    order = np.zeros(n, dtype=np.int32)
+    assert s.analyse(n, ptr, row, order, val=val, check=True).flag == 0
+    s.options.scaling = 3
+    inf = s.factorize(val, posdef=False)
+    assert inf.flag >= 0, inf.flag
+    x = s.solve(b)
+    be = gen.backward_error(n, ptr, row, val, x, b)
+    rc, mo, sc, pairs = sb.match_order(n, ptr, row, val)      # the scaling analyse saved
+    sym = s.symbolic()
+    ot = oracle_ref.OracleTree(sym)
+    ot.factor(val, False, scaling=np.ascontiguousarray(sc[sym["invp"] - 1]))
+    y = ot.solve_original(b * sc) * sc
+    beo = gen.backward_error(n, ptr, row, val, y, b)
+    assert inf.num_neg == ot.stats.num_neg
+    assert be <= 5e-14 and be <= 10 * max(beo, 2e-16), (be, beo)
+    s.options.scaling = 0
+    inf = s.factorize(val, posdef=False)
+    assert inf.flag in (8, 7), inf.flag                    # MATCH_ORD_NO_SCALE (or the singularity warning on top)
+    s.free(); ot.close()

@@ -117,3 +117,92 @@ def test_reference_c_example_builds_unchanged(lib):
             r = subprocess.run([exe], capture_output=True, text=True)
             # analyse (check + METIS) succeeds on the CPU; the factorization then fails loudly
             assert r.returncode in (0, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# options.ordering = 2: matching-based ordering (SPRAL match_order_metis)
+# ---------------------------------------------------------------------------------------------
+from oracle import match_order as omo                     # noqa: E402
+from test_scaling import badly_scaled, random_sym, row_inf_norms      # noqa: E402
+
+
+def _metis(nc, p3, r3):
+    return np.array([1], dtype=np.int32) if nc == 1 else sb.metis_order(nc, p3, r3)[0]
+
+
+def _check_match_order(n, ptr, row, val, rc, order, scale, pairs):
+    assert np.array_equal(np.sort(order), np.arange(1, n + 1))
+    for i in range(n):
+        p = int(pairs[i])
+        if p > 0:                                          # a 2x2 pivot: symmetric, adjacent in the order
+            assert pairs[p - 1] == i + 1
+            lo, hi = min(i + 1, p), max(i + 1, p)
+            assert order[hi - 1] == order[lo - 1] + 1
+        else:
+            assert p in (-1, -2)
+    assert (rc == 1) == bool((pairs == -2).any())         # unmatched variables <=> structurally singular
+    # MC64-type scaling: no scaled entry above 1, every matched row attains 1
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    a = np.abs(scale[row - 1] * val * scale[col])
+    assert (a < 1.0 + 5e-14).all()
+    mx = row_inf_norms(n, ptr, row, val, scale)
+    assert (mx[pairs != -2] >= 1.0 - 5e-14).all()
+    assert (scale[pairs == -2] == 0.0).all()              # exp(-huge): the reference's (dead) correction is not applied
+
+
+@pytest.mark.parametrize("kind,k,seed", [("lap7", 6, 1), ("kkt", 5, 3), ("lap27", 5, 2), ("kkt", 7, 4)])
+def test_match_order_on_the_benchmark_families(lib, kind, k, seed):
+    n, ptr, row, val = badly_scaled(kind, k, seed)
+    r = sb.match_order(n, ptr, row, val)
+    if r is None:
+        pytest.skip("library built without METIS")
+    rc, order, scale, pairs = r
+    f, o, s, p, _ = omo.match_order_metis(n, ptr, row, val, _metis)
+    assert (rc, f) == (0, 0)
+    assert np.array_equal(order, o) and np.array_equal(scale, s) and np.array_equal(pairs, p)
+    _check_match_order(n, ptr, row, val, rc, order, scale, pairs)
+    if kind == "kkt":
+        assert (pairs > 0).sum() >= 2 * (n // 4) * 0.9    # the pressure unknowns (zero diagonal) pair up
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_match_order_random_with_zero_diagonals(lib, seed):
+    rng = np.random.default_rng(600 + seed)
+    n = int(rng.integers(2, 70))
+    ptr, row, val = random_sym(n, 3 * n, rng, wide=bool(seed % 2))
+    col = np.repeat(np.arange(1, n + 1), np.diff(ptr))
+    val = val.copy()
+    val[(row == col) & (rng.random(len(row)) < 0.5)] = 0.0            # explicit zeros are dropped: forces 2x2 pivots
+    r = sb.match_order(n, ptr, row, val)
+    if r is None:
+        pytest.skip("library built without METIS")
+    rc, order, scale, pairs = r
+    f, o, s, p, _ = omo.match_order_metis(n, ptr, row, val, _metis)
+    assert rc == f
+    assert np.array_equal(order, o) and np.array_equal(scale, s) and np.array_equal(pairs, p)
+    nzmask = val != 0.0
+    # properties on the matrix without its explicit zeros
+    keep_ptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(col[nzmask] - 1, minlength=n))]).astype(np.int64)
+    _check_match_order(n, keep_ptr, row[nzmask], val[nzmask], rc, order, scale, pairs)
+
+
+def test_analyse_with_matching_based_ordering(lib):
+    n, ptr, row, val = badly_scaled("kkt", 5, 9)
+    if sb.match_order(n, ptr, row, val) is None:
+        pytest.skip("library built without METIS")
+    rc, order, scale, pairs = sb.match_order(n, ptr, row, val)
+    s = sb.Solver()
+    s.options.ordering = 2
+    out = np.zeros(n, dtype=np.int32)
+    inf = s.analyse(n, ptr, row, out, val=val, check=True)
+    assert inf.flag == 0
+    assert np.array_equal(np.sort(s.order), np.arange(1, n + 1))
+    s2 = sb.Solver()
+    inf2 = s2.analyse(n, ptr, row, order)                  # same tree as with the order supplied
+    assert (inf.num_factor, inf.num_flops) == (inf2.num_factor, inf2.num_flops)
+    # val is mandatory for this ordering
+    s3 = sb.Solver()
+    s3.options.ordering = 2
+    assert s3.analyse(n, ptr, row, out, val=None).flag == -9
+    for x in (s, s2, s3):
+        x.free()
