@@ -23,8 +23,8 @@ from sylver_b200 import gen, rb
 
 
 def pick_order(spec, n, ptr, row):
-    if spec == "metis":
-        return None                      # options.ordering = 1: computed by analyse
+    if spec in ("metis", "mc64-metis"):
+        return None                      # options.ordering = 1 / 2: computed by analyse
     if spec == "natural":
         return np.arange(1, n + 1, dtype=np.int32)
     if spec == "rcm":
@@ -47,8 +47,9 @@ def main(argv=None):
     g.add_argument("--indef", action="store_true")
     ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--nemin", type=int, default=32)
-    ap.add_argument("--scale", default="none", choices=["none", "mc64", "auction", "mc77"])
-    ap.add_argument("--order", default="metis")
+    ap.add_argument("--scale", default="none", choices=["none", "mc64", "auction", "mc77", "saved"])
+    ap.add_argument("--order", "--ordering", default="metis",
+                    help="metis | mc64-metis (matching-based, then --scale=saved is possible) | rcm | natural | FILE")
     ap.add_argument("--check", action="store_true", help="analyse with check=true (matrix cleaning)")
     ap.add_argument("--u", type=float, default=0.01)
     ap.add_argument("--failed-pivot-method", default="tpp", choices=["tpp", "pass"])
@@ -73,13 +74,13 @@ def main(argv=None):
     s = sb.Solver(ngpu=a.ngpu)
     s.options.nemin = a.nemin
     s.options.u = a.u
-    s.options.scaling = {"none": 0, "mc64": 1, "auction": 2, "mc77": 4}[a.scale]
+    s.options.scaling = {"none": 0, "mc64": 1, "auction": 2, "saved": 3, "mc77": 4}[a.scale]
     s.options.failed_pivot_method = 1 if a.failed_pivot_method == "tpp" else 2
     order = pick_order(a.order, n, ptr, row)
     if order is None:
         if sb.metis_order(3, np.array([1, 2, 3, 4]), np.array([1, 2, 3], dtype=np.int32)) is None:
             raise SystemExit("this build has no METIS: pass --order=rcm|natural|FILE")
-        s.options.ordering = 1
+        s.options.ordering = 2 if a.order == "mc64-metis" else 1
         order = np.zeros(n, dtype=np.int32)
     else:
         s.options.ordering = 0
