@@ -72,24 +72,17 @@ struct Mapper {
             for (int c : ch) assign_subtree(c, least_loaded(it.r0, it.r1));
             continue;
          }
-         // ranks per big child: largest remainder on shares proportional to flops, >= 1 each
-         double btot = 0;
-         for (int c : big) btot += wsub[c];
-         std::vector<int> share(big.size());
-         std::vector<std::pair<double, int>> rem;
-         int used = 0;
-         for (size_t i = 0; i < big.size(); ++i) {
-            const double s = nr * wsub[big[i]] / btot;
-            share[i] = std::max(1, (int)std::floor(s));
-            used += share[i];
-            rem.emplace_back(s - std::floor(s), (int)i);
+         // ranks per big child: one each, then every further rank goes to the child whose
+         // per-rank load (flops / ranks) is currently the largest -- the apportionment that
+         // minimises the maximum load (largest remainders can leave a child with 1.4x the
+         // average when two fractional parts nearly tie)
+         std::vector<int> share(big.size(), 1);
+         for (int used = (int)big.size(); used < nr; ++used) {
+            size_t best = 0;
+            for (size_t i = 1; i < big.size(); ++i)
+               if (wsub[big[i]] / share[i] > wsub[big[best]] / share[best]) best = i;
+            share[best]++;
          }
-         std::stable_sort(rem.begin(), rem.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
-            return a.first > b.first;
-         });
-         for (size_t i = 0; used < nr; ++i, ++used) share[rem[i % rem.size()].second]++;
-         for (size_t i = big.size(); used > nr && i-- > 0;)
-            while (share[i] > 1 && used > nr) { --share[i]; --used; }
          int r = it.r0;
          for (size_t i = 0; i < big.size(); ++i) {
             const int c = big[i];
