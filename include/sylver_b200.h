@@ -70,7 +70,7 @@ typedef struct {
                                  through the METIS 5 static library of the CUDA toolkit when the
                                  library was built with it, else flag -98 */
    int nemin;                 /* 32 */
-   bool prune_tree;           /* accepted, ignored: every front runs on the GPU */
+   bool prune_tree;           /* accepted, ignored: every front runs on the GPU (see the seam notes below) */
    long min_gpu_work;
    int scaling;               /* <=0: none / user supplied in `scale`; 1: Hungarian matching
                                  (MC64-like); 2: auction matching; >=4: norm equilibration
@@ -178,9 +178,20 @@ typedef struct {
 } sylver_inform_c;
 
 /* src/SymbolicTree.cxx:109-137.  All index arrays are 1-based and BORROWED
- * only during the call (the device plan copies what it needs).  subtrees /
- * small / contrib_dest / exec_loc may be NULL (nsubtrees must then be 0: the
- * B200 engine factorizes every front itself). */
+ * only during the call (the device plan copies what it needs).
+ *
+ * Pruned subtrees (the reference's options%prune_tree = .true., its default):
+ * the reference hands the nodes listed in `subtrees` to SSIDS through the
+ * spldlt_factor_subtree_c callback and receives their generated elements in
+ * child_contrib (src/tasks/tasks.hxx:459-513, src/kernels/contrib.cxx:14-38).
+ * The B200 engine has no delegate: the seam arrays describe EVERY node, so it
+ * factorizes the whole tree itself.  nsubtrees / subtrees / small /
+ * contrib_dest / exec_loc are therefore accepted and ignored (any of the
+ * arrays may be NULL), child_contrib of the numeric-tree constructors is never
+ * read or written, the callback is never called, and the spldlt_tree_solve_*
+ * entry points cover all nodes -- a Fortran caller must not run its own
+ * subtree factor/solve loops around them (INTEGRATION.md shows the guard), or,
+ * equivalently, must analyse with prune_tree = .false. (nsubtrees = 0). */
 void *spldlt_create_symbolic_tree(void *akeep, int n, int nnodes, int const *sptr,
                                   int const *sparent, long const *rptr,
                                   int const *rlist, long const *nptr,

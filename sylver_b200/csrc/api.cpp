@@ -31,6 +31,10 @@ struct AKeep {
    SymbolicTree* tree = nullptr;
    sylver_inform_t inform{};
    bool analysed = false;
+   // bumped by every spldlt_analyse on this handle: a numeric tree built against an earlier
+   // analysis (its SymbolicTree is gone) must be rebuilt, never refactored
+   // (the reference reuses akeep/fkeep across problems, sylver_ciface.F90:436-443,601-608)
+   unsigned long generation = 0;
    bool check = false;        // analyse(check = true): the matrix below replaces the caller's
    CleanMatrix clean;         // cleaned structure + conversion map (akeep%ptr/row/map/lmap)
    std::vector<double> match_scaling;   // options.ordering = 2: scaling saved for options.scaling = 3
@@ -39,6 +43,7 @@ struct AKeep {
 struct FKeep {
    NumericTree* tree = nullptr;
    AKeep* akeep = nullptr;
+   unsigned long generation = 0;   // akeep->generation the numeric tree was built against
    bool posdef = false;
    std::vector<double> scaling;   // in elimination order (empty if none)
    sylver_inform_t inform{};
@@ -137,6 +142,7 @@ void spldlt_analyse(int n, int* order, long const* ptr, int const* row, double c
       ak->clean = CleanMatrix();
       ak->match_scaling.clear();
    }
+   ++ak->generation;
    ak->check = check;
    if (n < 0) { inform->flag = SYLVER_ERROR_A_N_OOR; ak->inform = *inform; return; }
    if (!ptr || !row) { inform->flag = SYLVER_ERROR_PTR_ROW; ak->inform = *inform; return; }
@@ -322,13 +328,14 @@ void spldlt_factorize(bool posdef, long const* ptr, int const* row, double const
    const double* sc = fk->scaling.empty() ? nullptr : fk->scaling.data();
    // a numeric tree is built with or without a scaling buffer: rebuild it when that changes
    if (fk->tree && had_scaling != !fk->scaling.empty()) { numeric_tree_destroy(fk->tree); fk->tree = nullptr; }
-   if (fk->tree && fk->akeep == ak && fk->posdef == posdef) {
-      numeric_tree_refactor(fk->tree, val, sc, &stats);
+   if (fk->tree && fk->akeep == ak && fk->generation == ak->generation && fk->posdef == posdef) {
+      numeric_tree_refactor(fk->tree, val, sc, &copt, &stats);
    } else {
       if (fk->tree) { numeric_tree_destroy(fk->tree); fk->tree = nullptr; }
       fk->tree = numeric_tree_create(posdef, ak->tree, val, sc, &copt, &stats);
    }
    fk->akeep = ak;
+   fk->generation = ak->generation;
    fk->posdef = posdef;
    fold_stats(stats, inform);
    if (inform->flag >= 0 && n != inform->matrix_rank)
@@ -350,7 +357,8 @@ void spldlt_solve(int job, int nrhs, double* x, int ldx, void* akeep_v, void* fk
    if (fk->inform.flag < 0) { inform->flag = SYLVER_ERROR_CALL_SEQUENCE; return; }
    const int n = ak->sym.n;
    if (n == 0 || ak->sym.nnodes == 0) return;
-   if (!fk->tree) { inform->flag = SYLVER_ERROR_CALL_SEQUENCE; return; }
+   // factors of an earlier analysis on this akeep (re-analysed since): not usable
+   if (!fk->tree || fk->akeep != ak || fk->generation != ak->generation) { inform->flag = SYLVER_ERROR_CALL_SEQUENCE; return; }
    if (ldx < n || nrhs < 1) { inform->flag = SYLVER_ERROR_X_SIZE; return; }
    if (job < 0 || job > 4) { inform->flag = SYLVER_ERROR_JOB_OOR; return; }
    if (fk->posdef && (job == 2 || job == 4)) { inform->flag = SYLVER_ERROR_JOB_OOR; return; }
@@ -395,11 +403,9 @@ void* spldlt_create_symbolic_tree(void* akeep, int n, int nnodes, int const* spt
                                   long const* rptr, int const* rlist, long const* nptr, long const* nlist,
                                   int nsubtrees, int const* subtrees, int const* small, int const* contrib_dest,
                                   int const* exec_loc) {
-   (void)akeep; (void)subtrees; (void)small; (void)contrib_dest; (void)exec_loc;
-   if (nsubtrees != 0) {
-      fprintf(stderr, "sylver_b200: pruned subtrees are not delegated (nsubtrees must be 0; every front runs on the GPU)\n");
-      return nullptr;
-   }
+   // the subtree partition (prune_tree) is accepted and ignored: the arrays describe every node
+   // and the engine factorizes the whole tree itself (include/sylver_b200.h)
+   (void)akeep; (void)nsubtrees; (void)subtrees; (void)small; (void)contrib_dest; (void)exec_loc;
    int flag = 0;
    try {
       return symbolic_tree_create(n, nnodes, sptr, sparent, rptr, rlist, nptr, nlist, &flag);

@@ -138,7 +138,7 @@ extern "C" double sylver_b200_bench_dmma(int kind, int n, int k, int iters) {
       float best = 1e30f;
       for (int i = 0; i < iters + 1; ++i) {
          cudaEventRecord(e0);
-         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES>>>(T, b, 1, 0, 128, nullptr, 0, 0, 1);
+         k_gemm_batched<<<gemm_grid(1, tiles), GT_THREADS, GT_SMEM_BYTES>>>(T, b, 1, 0, 128, nullptr, 0, 0, 1);
          cudaEventRecord(e1);
          cudaEventSynchronize(e1);
          float ms; cudaEventElapsedTime(&ms, e0, e1);

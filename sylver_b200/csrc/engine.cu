@@ -843,7 +843,7 @@ static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launch
          if (m > p0 + pw) {
             const int tiles = (m - ((p0 + pw) & ~1) + GT_BM - 1) / GT_BM;
             ProfScope ps(nt, KC_TRSM, s2);
-            k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s2>>>(T, b, 2, si, nb, nt->d_Wsplit, wld, 0, 1);
+            k_gemm_batched<<<gemm_grid(2, tiles), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, b, 2, si, nb, nt->d_Wsplit, wld, 0, 1);
             ++launches;
          }
          CU_TRY(cudaMemcpy2DAsync(nt->d_stage, (size_t)rows * sizeof(double), Lf + (size_t)p0 * ldl + p0,
@@ -868,7 +868,7 @@ static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launch
          for (int tj = tstart; tj < TC; tj += tstep) tiles += TR - tj;
       if (tiles == 0) return;
       ProfScope ps(nt, KC_UPDATE);
-      k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, si, nb, nullptr, 0, tstart, tstep);
+      k_gemm_batched<<<gemm_grid(0, tiles), GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 0, si, nb, nullptr, 0, tstart, tstep);
       ++launches;
    };
    assemble(0);
@@ -901,7 +901,7 @@ static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launch
       for (int tj = q; tj < TR; tj += P) tiles += TR - tj;
       if (tiles > 0) {
          ProfScope ps(nt, KC_CONTRIB);
-         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, q, P);
+         k_gemm_batched<<<gemm_grid(1, tiles), GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, q, P);
          ++launches;
       }
    }
@@ -960,7 +960,7 @@ static void issue_posdef(NumericTree* nt) {
          if (ls.trsm_tiles == 0) return;
          TileBatch b{d_fr, nt->d_prefix + ls.trsm_prefix, ls.cnt};
          ProfScope ps(nt, KC_TRSM, q);
-         k_gemm_batched<<<ls.trsm_tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld, 0, 1);
+         k_gemm_batched<<<gemm_grid(2, ls.trsm_tiles), GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 2, (int)si, nb, nt->d_W, ls.wld, 0, 1);
          ++launches;
       };
       auto update = [&](size_t si, int sub, cudaStream_t q) {
@@ -970,7 +970,7 @@ static void issue_posdef(NumericTree* nt) {
          const size_t off = sub == 0 ? ls.upd_prefix : (sub == 1 ? ls.updn_prefix : ls.updr_prefix);
          TileBatch b{d_fr, nt->d_prefix + off, ls.cnt};
          ProfScope ps(nt, KC_UPDATE, q);
-         k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, (int)si, nb, nullptr, 0, sub == 2 ? 1 : 0, 1);
+         k_gemm_batched<<<gemm_grid(0, tiles), GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, (int)si, nb, nullptr, 0, sub == 2 ? 1 : 0, 1);
          ++launches;
       };
       // Look-ahead (few, large fronts): as soon as the next block column has received its
@@ -988,7 +988,7 @@ static void issue_posdef(NumericTree* nt) {
             if (tiles == 0) return;
             TileBatch b{d_fr, nt->d_prefix + off, ls.cnt};
             ProfScope ps(nt, KC_UPDATE, q);
-            k_gemm_batched<<<tiles, GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, kstep, knb, nullptr, 0, tstart, 1);
+            k_gemm_batched<<<gemm_grid(0, tiles), GT_THREADS, GT_SMEM_BYTES, q>>>(T, b, 0, kstep, knb, nullptr, 0, tstart, 1);
             ++launches;
          };
          auto chain = [&](size_t si, cudaStream_t q) {
@@ -1045,7 +1045,7 @@ static void issue_posdef(NumericTree* nt) {
       if (lp.contrib_tiles > 0) {
          TileBatch b{d_fr, nt->d_prefix + lp.contrib_prefix, lp.count};
          ProfScope ps(nt, KC_CONTRIB);
-         k_gemm_batched<<<lp.contrib_tiles, GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, 0, 1);
+         k_gemm_batched<<<gemm_grid(1, lp.contrib_tiles), GT_THREADS, GT_SMEM_BYTES, s>>>(T, b, 1, 0, nb, nullptr, 0, 0, 1);
          ++launches;
       }
       assemble(1);      // children -> contribution block (after this front's own Schur complement)
@@ -1212,8 +1212,10 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
    return nt;
 }
 
-void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* scaling, sylver_inform_c* stats) {
+void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* scaling,
+                           const sylver_options_c* options, sylver_inform_c* stats) {
    auto w0 = std::chrono::steady_clock::now();
+   if (options) nt->opt = *options;
    try {
       load_values(nt, aval, scaling);
       if (nt->posdef) run_posdef(nt, stats);

@@ -83,9 +83,10 @@ void plan_exchanges(const SymbolicTree& st, const std::vector<int>& owner, int r
 
 NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* aval, const double* scaling,
                                  const sylver_options_c* options, sylver_inform_c* stats);
-// Re-run the factorization with new values on an existing tree (same plan).
+// Re-run the factorization with new values on an existing tree (same plan); the options are
+// read again on every call like the reference does (u, small, pivot methods, action).
 void numeric_tree_refactor(NumericTree* nt, const double* aval, const double* scaling,
-                           sylver_inform_c* stats);
+                           const sylver_options_c* options, sylver_inform_c* stats);
 void numeric_tree_destroy(NumericTree* nt);
 // job: 1 fwd, 2 diag, 3 bwd, 4 diag+bwd, 0 all.  x host or device, already permuted.
 int numeric_tree_solve(const NumericTree* nt, int job, int nrhs, double* x, int ldx);

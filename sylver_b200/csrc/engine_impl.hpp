@@ -217,6 +217,8 @@ struct NumericTree {
    void* d_lvl = nullptr;                // per-level upload buffer (geometry updates, orders, prefixes)
    void* h_lvl = nullptr;                // pinned mirror
    size_t lvl_cap = 0;
+   cudaEvent_t ev_lvl = nullptr;         // completion of the last H2D copy out of h_lvl
+   bool lvl_busy = false;
    int* d_lvl_out = nullptr;             // nelim of the level's fronts (read back per level)
    int* h_lvl_out = nullptr;
    size_t lvl_out_cap = 0;

@@ -104,6 +104,7 @@ void indef_setup(NumericTree* nt) {
    CU_TRY(cudaMalloc(&nt->d_state, N * sizeof(FrontState)));
    CU_TRY(cudaMalloc(&nt->d_nelim, N * sizeof(int)));
    CU_TRY(cudaMalloc(&nt->d_stats, 8 * sizeof(int)));
+   CU_TRY(cudaEventCreateWithFlags(&nt->ev_lvl, cudaEventDisableTiming));
    nt->d_ldc = dev_upload(nt->ldc);
    nt->d_coff = dev_upload(nt->coff);
    nt->d_ncol0 = dev_upload(st->ncol);
@@ -127,6 +128,8 @@ void indef_destroy(NumericTree* nt) {
    cudaFree(nt->d_lvl); cudaFree(nt->d_lvl_out);
    if (nt->h_lvl) cudaFreeHost(nt->h_lvl);
    if (nt->h_lvl_out) cudaFreeHost(nt->h_lvl_out);
+   if (nt->ev_lvl) cudaEventDestroy(nt->ev_lvl);
+   nt->ev_lvl = nullptr; nt->lvl_busy = false;
    nt->d_ncol0 = nullptr; nt->d_woff = nt->d_doff = nt->d_permoff = nullptr;
    nt->d_state = nullptr; nt->d_nelim = nt->d_stats = nullptr; nt->d_diag = nullptr;
    nt->d_lvl = nullptr; nt->h_lvl = nullptr; nt->d_lvl_out = nullptr; nt->h_lvl_out = nullptr;
@@ -160,8 +163,12 @@ static void upload_level_buffer(NumericTree* nt, const Packer& pk) {
       CU_TRY(cudaMallocHost(&nt->h_lvl, cap));
    }
    if (pk.buf.empty()) return;
+   // the previous upload may still be reading the pinned mirror (and kernels the device copy)
+   if (nt->lvl_busy) CU_TRY(cudaEventSynchronize(nt->ev_lvl));
    memcpy(nt->h_lvl, pk.buf.data(), pk.buf.size());
    CU_TRY(cudaMemcpyAsync(nt->d_lvl, nt->h_lvl, pk.buf.size(), cudaMemcpyHostToDevice, s));
+   CU_TRY(cudaEventRecord(nt->ev_lvl, s));
+   nt->lvl_busy = true;
 }
 
 // Hand-over of one level's results to the ranks that own the parents (multi-rank runs):
@@ -454,7 +461,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                   // rest of the panel, including the columns that just failed (CTAs of fronts
                   // with nothing left in the panel exit at once)
                   ProfScope ps(nt, KC_TRSM);
-                  k_gemm_batched<<<inn_prefix[cnt_s], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
+                  k_gemm_batched<<<gemm_grid(3, inn_prefix[cnt_s]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
                   ++launches;
                }
             }
@@ -462,7 +469,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                // columns behind the panel exist (more candidates, or failed columns of earlier panels)
                TileBatch ub{d_fr, d_upd, cnt_o};
                ProfScope ps(nt, KC_UPDATE);
-               k_gemm_batched<<<upd_prefix[cnt_o], GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 5, 0, IB, nullptr, 0, 0, 1);
+               k_gemm_batched<<<gemm_grid(5, upd_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 5, 0, IB, nullptr, 0, 0, 1);
                k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr);
                launches += 2;
             } else {
@@ -479,7 +486,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          if (con_prefix[cnt] > 0) {
             TileBatch cb{d_fr, d_con, cnt};
             ProfScope ps(nt, KC_CONTRIB);
-            k_gemm_batched<<<con_prefix[cnt], GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0, 0, 1);
+            k_gemm_batched<<<gemm_grid(4, con_prefix[cnt]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0, 0, 1);
             ++launches;
          }
          assemble(1);

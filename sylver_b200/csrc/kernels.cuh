@@ -133,190 +133,158 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // ---------------------------------------------------------------------------
-// Tiled DMMA  C(128x128) (+)= -A(128xK) * B(128xK)^T   ("NT" rank-K update)
+// Tiled DMMA  C(128x64) (+)= -A(128xK) * B(64xK)^T   ("NT" rank-K update)
 //
 // Replaces update_block / update_contrib_block / form_contrib
 // (reference src/kernels/factor.hxx:149-263, src/kernels/factor_indef.hxx:23-49,
 // 201-342; GPU variants src/StarPU/cuda/kernels.hxx:45-182) and, with the
 // inverted diagonal block as B, solve_block (src/kernels/factor.hxx:95-138).
 //
-// Both operands are column-major panels (row index contiguous), staged into
-// shared memory k-column by k-column with TMA bulk copies through a 4-stage
-// mbarrier pipeline by one producer warp; 8 consumer warps (4 x 2, 32 x 64 per
-// warp) issue DMMA.8x8x4 from conflict-free padded shared memory.
+// The host work lists count 128 x 128 tiles of a lower-triangular tile grid; every tile is
+// computed by TWO CTAs (one per 64-column half, adjacent block indices so that they share the
+// A panel in L2) and two CTAs are resident per SM (2 x 100 KB of shared memory, 2 x 8 warps at
+// <= 128 registers): while one CTA reads and writes its destination tile (the read-modify-write
+// epilogue of a rank-256 update is a fifth of the tile's life) the other one keeps the FP64
+// tensor pipe busy, and the tail of a launch drains at half-tile granularity.
+//
+// Both operands are column-major panels (row index contiguous), staged into shared memory
+// k-column by k-column with TMA bulk copies (cp.async.bulk, one per k-column and operand,
+// into padded conflict-free rows) through a 4-stage mbarrier pipeline.  There is no producer
+// warp: warp 0 issues the copies of k-block kb + 2 before it consumes block kb (a 17th warp
+// would cap the kernel at 96 registers).  8 warps (4 x 2, 32 x 32 each) issue DMMA.8x8x4 with
+// the front COLUMN as the MMA row index, so that a lane ends up with two vertically adjacent
+// entries of the column-major destination: the epilogue reads and writes the destination
+// straight from the accumulator registers with 16-byte accesses in full 64-byte segments.
 // ---------------------------------------------------------------------------
 constexpr int GT_BM = 128;             // tile rows
-constexpr int GT_BN = 128;             // tile cols
+constexpr int GT_BN = 128;             // width of a tile-grid column (two CTAs of GT_HN columns)
+constexpr int GT_HN = 64;              // columns per CTA
 constexpr int GT_KT = 16;              // k-columns per stage
-constexpr int GT_LDS = 132;            // padded smem row stride (132 mod 16 == 4: conflict free)
+constexpr int GT_LDA = 132;            // padded smem row strides (mod 16 == 4: conflict free)
+constexpr int GT_LDB = 68;
 constexpr int GT_STAGES = 4;
-constexpr int GT_CONSUMERS = 16;       // warps, 4 (M) x 4 (N), 32 x 32 each: 4 per SM sub-partition
-constexpr int GT_THREADS = (GT_CONSUMERS + 1) * 32;
-constexpr int GT_LDC = 130;            // epilogue staging stride (130 mod 8 == 2: conflict free)
-constexpr size_t GT_STAGE_DOUBLES = 2 * GT_KT * GT_LDS;
+constexpr int GT_LOOKAHEAD = 2;        // k-blocks in flight ahead of the one being consumed
+constexpr int GT_WARPS = 8;            // 4 (rows) x 2 (columns), 32 x 32 each
+constexpr int GT_THREADS = GT_WARPS * 32;
+constexpr size_t GT_STAGE_DOUBLES = (size_t)GT_KT * (GT_LDA + GT_LDB);
 constexpr size_t GT_SMEM_BYTES = GT_STAGES * GT_STAGE_DOUBLES * sizeof(double) + 2 * GT_STAGES * sizeof(uint64_t);
-static_assert((size_t)GT_BN * GT_LDC <= GT_STAGES * GT_STAGE_DOUBLES, "epilogue tile must fit in the pipeline buffers");
+static_assert(2 * (GT_SMEM_BYTES + 1024) <= 232448, "two CTAs per SM");
+
+// CTAs of a launch that covers `tiles` 128 x 128 tiles (mode 2 keeps one CTA per tile)
+static inline int gemm_grid(int mode, int tiles) { return mode == 2 ? tiles : 2 * tiles; }
 
 struct GemmTile {
-   const double* A;   // first row of the A operand tile, k = 0 column
-   const double* B;   // first row of the B operand tile, k = 0 column
+   const double* A;   // row operand: first row of the tile, k = 0 column
+   const double* B;   // column operand: first column of the CTA's half, k = 0 column
    int lda, ldb;      // column strides (doubles)
-   int arows, brows;  // valid rows (<=128) in each operand tile (rounded up to even inside)
+   int arows, brows;  // valid rows (<= 128) / columns (<= 64) of the tile
    int K;             // depth
-   // destination tile (for the L2 prefetch issued by the producer warp): column c of the
-   // tile starts at dst + c*ldd; rows [0,128) -- only when prefetch is set
-   const double* dst;
-   int ldd;
-   bool prefetch;
-   int pf_c0, pf_c1;  // tile-relative column range worth prefetching
-   int pf_lines;      // 128 B lines per column
-   // fused extend-add (contribution tiles): the children's entries the epilogue gathers are
-   // pulled into L2 by the producer warp while the tensor cores work
-   const double* gsrc[2];
-   const int* gmap[2];    // parent contribution row -> child row (-1: none), increasing
-   int gld[2];
-   int g_r0, g_c0;        // contribution-relative row / column of the tile origin
-   int g_k;               // order of the parent's contribution block
 };
 
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMERS * 32) : "memory"); }
+struct GemmPipe {
+   double* smem;
+   uint64_t* full;
+   uint64_t* empty;
+   int gk;            // k-blocks that went through the pipeline so far (phase bookkeeping)
+};
 
-// Runs the pipeline; on return (consumer warps) the 128 x 128 product tile is staged in
-// shared memory as Cs[c*GT_LDC + r] and the consumer warps are synchronised.  Returns false
-// for the producer warp (which has nothing left to do).
-__device__ __forceinline__ bool gemm_tile_mainloop(const GemmTile& t, double* smem) {
-   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_DOUBLES);
-   uint64_t* empty = full + GT_STAGES;
-   const int warp = threadIdx.x >> 5;
-   const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void gemm_pipe_init(GemmPipe& p, double* smem) {
+   p.smem = smem;
+   p.full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_DOUBLES);
+   p.empty = p.full + GT_STAGES;
+   p.gk = 0;
    if (threadIdx.x == 0) {
       for (int s = 0; s < GT_STAGES; ++s) {
-         mbar_init(&full[s], 1);
-         mbar_init(&empty[s], GT_CONSUMERS);
+         mbar_init(&p.full[s], 1);
+         mbar_init(&p.empty[s], GT_WARPS);
       }
       mbar_fence_init();
    }
    __syncthreads();
-   const int nk = (t.K + GT_KT - 1) / GT_KT;
-   const bool same = (t.A == t.B) && (t.lda == t.ldb);   // diagonal tile: stage the panel once
-   if (warp == GT_CONSUMERS) {
-      // ===== producer warp: lane l < 16 copies A column l, lane 16+l copies B column l =====
-      const uint32_t abytes = (uint32_t)(((t.arows + 1) & ~1) * sizeof(double));
-      const uint32_t bbytes = (uint32_t)(((t.brows + 1) & ~1) * sizeof(double));
-      for (int kb = 0; kb < nk; ++kb) {
-         const int s = kb % GT_STAGES;
-         const uint32_t ph = (kb / GT_STAGES) & 1;
-         mbar_wait(&empty[s], ph ^ 1);
-         const int k0 = kb * GT_KT;
-         const int kv = min(GT_KT, t.K - k0);           // valid k-columns in this stage
-         double* As = smem + s * GT_STAGE_DOUBLES;
-         double* Bs = As + GT_KT * GT_LDS;
-         const int kc = lane & 15;
-         const bool isB = lane >= 16;
-         if (kc >= kv && kc < ((kv + 3) & ~3)) {
-            // zero-fill the tail of a partial k-group (generic proxy; ordered by the arrive below)
-            double* dst = (isB ? Bs : As) + kc * GT_LDS;
-            if (!(isB && same))
-               for (int r = 0; r < GT_BM; ++r) dst[r] = 0.0;
-         }
-         __syncwarp();
-         if (lane == 0) mbar_expect_tx(&full[s], kv * (abytes + (same ? 0u : bbytes)));
-         __syncwarp();
-         if (kc < kv) {
-            if (!isB)
-               tma_bulk_g2s(As + kc * GT_LDS, t.A + (size_t)(k0 + kc) * t.lda, abytes, &full[s]);
-            else if (!same)
-               tma_bulk_g2s(Bs + kc * GT_LDS, t.B + (size_t)(k0 + kc) * t.ldb, bbytes, &full[s]);
-         }
-         if (kb == min(nk, GT_STAGES) - 1 && (t.gsrc[0] || t.gsrc[1])) {
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-               if (!t.gsrc[s2]) continue;
-               // child rows hit by this tile's rows: [rlo, rhi]
-               int rlo = 0x7fffffff, rhi = -1;
-#pragma unroll
-               for (int q = 0; q < 4; ++q) {
-                  const int r = t.g_r0 + lane + 32 * q;
-                  const int v = (r >= 0 && r < t.g_k) ? t.gmap[s2][r] : -1;
-                  if (v >= 0) { rlo = min(rlo, v); rhi = max(rhi, v); }
-               }
-#pragma unroll
-               for (int o = 16; o > 0; o >>= 1) {
-                  rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
-                  rhi = max(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
-               }
-               if (rhi < 0) continue;
-               for (int cc = lane; cc < GT_BN; cc += 32) {
-                  const int c = t.g_c0 + cc;
-                  const int ic = (c >= 0 && c < t.g_k) ? t.gmap[s2][c] : -1;
-                  if (ic < 0) continue;
-                  const int lo = max(rlo, ic);
-                  if (lo > rhi) continue;
-                  const char* p0 = reinterpret_cast<const char*>(t.gsrc[s2] + (size_t)ic * t.gld[s2] + lo);
-                  const char* p1 = reinterpret_cast<const char*>(t.gsrc[s2] + (size_t)ic * t.gld[s2] + rhi);
-                  for (const char* p = p0; p <= p1; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
-               }
-            }
-         }
-         if (kb == min(nk, GT_STAGES) - 1 && t.prefetch) {
-            // pull the destination tile into L2 while the tensor cores work
-            for (int c = t.pf_c0 + lane; c < t.pf_c1; c += 32) {
-               const char* p = reinterpret_cast<const char*>(t.dst + (size_t)c * t.ldd);
-               for (int q = 0; q < t.pf_lines; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + q * 128));
-            }
-         }
+}
+
+// warp 0: stage k-block kb of the tile (lane l < 16 copies A column l, lane 16 + l B column l)
+__device__ __forceinline__ void gemm_issue_block(const GemmPipe& p, const GemmTile& t, int kb, bool share, int lane) {
+   const int G = p.gk + kb;
+   const int s = G % GT_STAGES;
+   if (G >= GT_STAGES) mbar_wait(&p.empty[s], ((G / GT_STAGES) - 1) & 1);
+   const int k0 = kb * GT_KT;
+   const int kv = min(GT_KT, t.K - k0);           // valid k-columns in this stage
+   double* As = p.smem + s * GT_STAGE_DOUBLES;
+   double* Bs = As + GT_KT * GT_LDA;
+   const int kc = lane & 15;
+   const bool isB = lane >= 16;
+   const uint32_t abytes = (uint32_t)(((t.arows + 1) & ~1) * sizeof(double));
+   const uint32_t bbytes = (uint32_t)(((t.brows + 1) & ~1) * sizeof(double));
+   if (kc >= kv && kc < ((kv + 3) & ~3)) {
+      // zero-fill the tail of a partial k-group (generic proxy; ordered by the arrive below)
+      if (!isB) {
+         double* dst = As + kc * GT_LDA;
+         for (int r = 0; r < GT_BM; ++r) dst[r] = 0.0;
+      } else if (!share) {
+         double* dst = Bs + kc * GT_LDB;
+         for (int r = 0; r < GT_HN; ++r) dst[r] = 0.0;
       }
-      return false;
    }
-   // ===== consumer warps =====
+   __syncwarp();
+   if (lane == 0) mbar_expect_tx(&p.full[s], kv * (abytes + (share ? 0u : bbytes)));
+   __syncwarp();
+   if (kc < kv) {
+      if (!isB)
+         tma_bulk_g2s(As + kc * GT_LDA, t.A + (size_t)(k0 + kc) * t.lda, abytes, &p.full[s]);
+      else if (!share)
+         tma_bulk_g2s(Bs + kc * GT_LDB, t.B + (size_t)(k0 + kc) * t.ldb, bbytes, &p.full[s]);
+   }
+}
+
+// Accumulates the product tile: acc[ic][jr][h] = sum_k B[col][k] A[row][k] with
+//   col = wn*32 + ic*8 + g,  row = wm*32 + jr*8 + 2*tq + h      (lane = 4*g + tq).
+// `active` warps compute; the others only keep the pipeline's barriers moving.
+__device__ __forceinline__ void gemm_tile_mainloop(GemmPipe& p, const GemmTile& t, bool active, double (&acc)[4][4][2]) {
+   const int warp = threadIdx.x >> 5;
+   const int lane = threadIdx.x & 31;
+   const int nk = (t.K + GT_KT - 1) / GT_KT;
+   const bool share = (t.A == t.B) && (t.lda == t.ldb);   // diagonal tile: the columns are rows of A
    const int wm = warp & 3, wn = warp >> 2;
    const int g = lane >> 2, tq = lane & 3;
-   double acc[4][4][2];
 #pragma unroll
    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+   if (warp == 0)
+      for (int kb = 0; kb < min(nk, GT_LOOKAHEAD); ++kb) gemm_issue_block(p, t, kb, share, lane);
    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % GT_STAGES;
-      const uint32_t ph = (kb / GT_STAGES) & 1;
-      mbar_wait(&full[s], ph);
-      const double* As = smem + s * GT_STAGE_DOUBLES;
-      const double* Bs = same ? As : As + GT_KT * GT_LDS;
-      const int kv = min(GT_KT, t.K - kb * GT_KT);
-      const int kg = (kv + 3) >> 2;
-      const double* ap = As + tq * GT_LDS + wm * 32 + g;
-      const double* bp = Bs + tq * GT_LDS + wn * 32 + g;
+      if (warp == 0 && kb + GT_LOOKAHEAD < nk) gemm_issue_block(p, t, kb + GT_LOOKAHEAD, share, lane);
+      const int G = p.gk + kb;
+      const int s = G % GT_STAGES;
+      mbar_wait(&p.full[s], (G / GT_STAGES) & 1);
+      if (active) {
+         const double* As = p.smem + s * GT_STAGE_DOUBLES;
+         const double* Bs = share ? As : As + GT_KT * GT_LDA;
+         const int ldb = share ? GT_LDA : GT_LDB;
+         const int kv = min(GT_KT, t.K - kb * GT_KT);
+         const int kg = (kv + 3) >> 2;
+         const double* rp = As + tq * GT_LDA + wm * 32 + g;
+         const double* cp = Bs + tq * ldb + wn * 32 + g;
 #pragma unroll 1
-      for (int k4 = 0; k4 < kg; ++k4) {
-         double a[4], b[4];
+         for (int k4 = 0; k4 < kg; ++k4) {
+            double rf[4], cf[4];
 #pragma unroll
-         for (int i = 0; i < 4; ++i) a[i] = ap[i * 8];
+            for (int i = 0; i < 4; ++i) cf[i] = cp[i * 8];
 #pragma unroll
-         for (int j = 0; j < 4; ++j) b[j] = bp[j * 8];
+            for (int j = 0; j < 4; ++j) rf[j] = rp[j * 8];
 #pragma unroll
-         for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-         ap += 4 * GT_LDS;
-         bp += 4 * GT_LDS;
+               for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], cf[i], rf[j]);
+            rp += 4 * GT_LDA;
+            cp += 4 * ldb;
+         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (lane == 0) mbar_arrive(&p.empty[s]);
    }
-   // every stage has been consumed by this warp; once all consumers are here the pipeline
-   // buffers are dead and can hold the output tile
-   consumer_bar();
-#pragma unroll
-   for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-         double* col = smem + (size_t)(wn * 32 + j * 8 + 2 * tq + h) * GT_LDC + wm * 32 + g;
-#pragma unroll
-         for (int i = 0; i < 4; ++i) col[i * 8] = acc[i][j][h];
-      }
-   consumer_bar();
-   return true;
+   p.gk += nk;
 }
 
 // Work descriptor of one batched launch: the participating fronts and an
@@ -336,20 +304,194 @@ __device__ __forceinline__ int find_front(const TileBatch& b, int item) {
    return lo;
 }
 
+// Destination of a tile: element (r, c) (absolute front indices) lives at dbase + c*ldd + r and is
+// valid iff  c in [clo, chi),  r in [max(rmin, lower ? c : 0), m).
+struct GemmDest {
+   double* dbase;
+   int ldd, clo, chi, rmin, m;
+   bool lower;
+   int op;              // 0: dst -= v   1: dst = gathered children - v   2: dst = v
+   // fused extend-add (contribution tiles, op 1): up to two children whose generated elements
+   // are gathered through parent-contribution-row -> child-row maps (-1: none, increasing)
+   const double* gsrc[2];
+   const int* gmap[2];
+   int gld[2];
+   int n;               // first contribution row/column of the front
+};
+
+// Epilogue of one warp's 32 x 32 block, straight from the accumulator registers.
+__device__ __forceinline__ void gemm_tile_epilogue(const GemmDest& d, int i0, int j0, const double (&acc)[4][4][2]) {
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int wm = warp & 3, wn = warp >> 2;
+   const int g = lane >> 2, tq = lane & 3;
+   const int rb = i0 + wm * 32 + 2 * tq;        // + jr*8 + h
+   const int cb = j0 + wn * 32 + g;             // + ic*8
+   const int rlo = i0 + wm * 32, clo_w = j0 + wn * 32;
+   // the whole 32 x 32 block valid?
+   const bool interior = (rlo + 32 <= d.m) && (clo_w >= d.clo) && (clo_w + 32 <= d.chi) && (rlo >= d.rmin) &&
+                         (!d.lower || rlo >= clo_w + 31);
+   const bool vec = ((reinterpret_cast<uintptr_t>(d.dbase + rb) & 15) == 0) && ((d.ldd & 1) == 0);
+   const bool fused = d.op == 1 && (d.gsrc[0] || d.gsrc[1]);
+   int fir[2][4][2], fic[2][4];
+   if (fused) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+#pragma unroll
+         for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+               const int r = rb + jr * 8 + h;
+               fir[s][jr][h] = (d.gsrc[s] && r >= d.n && r < d.m) ? d.gmap[s][r - d.n] : -1;
+            }
+#pragma unroll
+         for (int ic = 0; ic < 4; ++ic) {
+            const int c = cb + ic * 8;
+            fic[s][ic] = (d.gsrc[s] && c >= d.n && c < d.m) ? d.gmap[s][c - d.n] : -1;
+         }
+      }
+   }
+#pragma unroll
+   for (int ic0 = 0; ic0 < 4; ic0 += 2) {
+      double v[2][4][2];
+      bool ok[2][4][2];
+      double* colp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+         const int ic = ic0 + u;
+         const int c = cb + ic * 8;
+         const bool cok = interior || (c >= d.clo && c < d.chi);
+         colp[u] = d.dbase + (size_t)c * d.ldd;
+#pragma unroll
+         for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+               const int r = rb + jr * 8 + h;
+               ok[u][jr][h] = interior || (cok && r < d.m && r >= d.rmin && (!d.lower || r >= c));
+               v[u][jr][h] = acc[ic][jr][h];
+            }
+      }
+      if (fused) {
+#pragma unroll
+         for (int s = 0; s < 2; ++s) {
+            if (!d.gsrc[s]) continue;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+               const int icc = fic[s][ic0 + u];
+               const double* col = d.gsrc[s] + (size_t)max(icc, 0) * d.gld[s];
+#pragma unroll
+               for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                     const bool hit = icc >= 0 && fir[s][jr][h] >= icc;      // maps are increasing: row >= col
+                     const double gv = hit ? col[fir[s][jr][h]] : 0.0;
+                     v[u][jr][h] -= gv;
+                  }
+            }
+         }
+      }
+      if (d.op == 0) {
+         // read-modify-write: all loads of the batch first (8 x 16 B in flight per lane)
+         double q[2][4][2];
+#pragma unroll
+         for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int jr = 0; jr < 4; ++jr) {
+               double* ptr = colp[u] + rb + jr * 8;
+               if (vec && ok[u][jr][0] && ok[u][jr][1]) {
+                  const double2 x = *reinterpret_cast<const double2*>(ptr);
+                  q[u][jr][0] = x.x; q[u][jr][1] = x.y;
+               } else {
+                  q[u][jr][0] = ok[u][jr][0] ? ptr[0] : 0.0;
+                  q[u][jr][1] = ok[u][jr][1] ? ptr[1] : 0.0;
+               }
+            }
+#pragma unroll
+         for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int jr = 0; jr < 4; ++jr) {
+               v[u][jr][0] = q[u][jr][0] - v[u][jr][0];
+               v[u][jr][1] = q[u][jr][1] - v[u][jr][1];
+            }
+      } else if (d.op == 1) {
+#pragma unroll
+         for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int jr = 0; jr < 4; ++jr) { v[u][jr][0] = -v[u][jr][0]; v[u][jr][1] = -v[u][jr][1]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+         for (int jr = 0; jr < 4; ++jr) {
+            double* ptr = colp[u] + rb + jr * 8;
+            if (vec && ok[u][jr][0] && ok[u][jr][1]) {
+               *reinterpret_cast<double2*>(ptr) = make_double2(v[u][jr][0], v[u][jr][1]);
+            } else {
+               if (ok[u][jr][0]) ptr[0] = v[u][jr][0];
+               if (ok[u][jr][1]) ptr[1] = v[u][jr][1];
+            }
+         }
+   }
+}
+
+// Pull what the epilogue of this warp will touch into L2 while the tensor cores work: the
+// destination block (read-modify-write modes) or the children's entries it gathers.
+__device__ __forceinline__ void gemm_tile_prefetch(const GemmDest& d, int i0, int j0) {
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int wm = warp & 3, wn = warp >> 2;
+   const int r0 = i0 + wm * 32, c = j0 + wn * 32 + lane;
+   if (d.op == 0) {
+      if (c >= d.clo && c < d.chi) {
+         const int ra = max(r0, max(d.rmin, d.lower ? c : 0)), rz = min(r0 + 32, d.m);
+         if (ra < rz) {
+            const char* p0 = reinterpret_cast<const char*>(d.dbase + (size_t)c * d.ldd + ra);
+            const char* p1 = reinterpret_cast<const char*>(d.dbase + (size_t)c * d.ldd + rz - 1);
+            for (const char* p = p0; p <= p1; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+         }
+      }
+   } else if (d.op == 1 && (d.gsrc[0] || d.gsrc[1])) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+         if (!d.gsrc[s]) continue;
+         const int r = r0 + lane;
+         int lo = (r >= d.n && r < d.m) ? d.gmap[s][r - d.n] : -1;
+         int hi = lo;
+         if (lo < 0) lo = 0x7fffffff;
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+         }
+         if (hi < 0) continue;
+         const int ic = (c >= d.n && c < d.m) ? d.gmap[s][c - d.n] : -1;
+         if (ic < 0) continue;
+         const int a = max(lo, ic);
+         if (a > hi) continue;
+         const char* p0 = reinterpret_cast<const char*>(d.gsrc[s] + (size_t)ic * d.gld[s] + a);
+         const char* p1 = reinterpret_cast<const char*>(d.gsrc[s] + (size_t)ic * d.gld[s] + hi);
+         for (const char* p = p0; p <= p1; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+         asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+      }
+   }
+}
+
 // mode 0: trailing update inside the L panel after block column [p0, p0+pw):
 //         L[r][c] -= sum_k L[r][k] L[c][k],  c in [p0+pw, n), r in [c, m)
-// mode 1: contribution block:  C[r-n][c-n] = beta*C - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
-// mode 2: panel solve with the inverted diagonal block W (pw x pw, ld wld):
-//         L[r][p0+c] = sum_k L[r][p0+k] W[c][k],  r in [p0+pw, m)
+// mode 1: contribution block:  C[r-n][c-n] = (children) - sum_{k<n} L[r][k] L[c][k], n <= c <= r < m
+// mode 2: panel solve with the inverted diagonal block W (pw x pw lower triangular, ld wld):
+//         L[r][p0+c] = sum_{k<=c} L[r][p0+k] W[c][k],  r in [p0+pw, m)   (in place: one CTA per
+//         128-row tile does the right half first, then the left half, which reads only its own
+//         64 columns)
 // nb is the block-column width; `step` the block column index.  Modes 0 and 1 enumerate the
 // tile columns tstart, tstart + tstep, ... of the tile grid (look-ahead scheduling: the grid
 // size limits a launch to the first tile column, tstart = 1 skips it; split fronts: the tile
-// columns this rank owns).
-static __global__ void __launch_bounds__(GT_THREADS, 1)
+// columns this rank owns).  Launch gemm_grid(mode, tiles) CTAs.
+static __global__ void __launch_bounds__(GT_THREADS, 2)
 k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld,
                int tstart, int tstep) {
    extern __shared__ __align__(128) double smem[];
-   const int item = blockIdx.x;
+   const int half = (mode == 2) ? 0 : (blockIdx.x & 1);
+   const int item = (mode == 2) ? blockIdx.x : (blockIdx.x >> 1);
    const int fi = find_front(batch, item);
    const int f = batch.fronts[fi];
    int local = item - batch.prefix[fi];
@@ -357,15 +499,39 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    double* Lf = T.L + T.loff[f];
    const int p0 = step * nb;
    const int pw = min(nb, n - p0);
+   const int warp = threadIdx.x >> 5;
+   const int wm = warp & 3, wn = warp >> 2;
 
    GemmTile t;
-   int i0, j0;          // absolute front row / column of the tile origin
-   // destination addressing: element (r, c) of the tile (absolute front indices) lives at
-   // dbase + c*ldd + r ; valid iff  r in [rlo(c), m)  and  c in [clo, chi)
-   double* dbase;
-   int ldd, clo, chi, rmin;
-   bool lower;          // additionally require r >= c
-   int op;              // 0: dst -= v   1: dst = -v   2: dst = v
+   GemmDest d;
+   d.m = m; d.n = n;
+   d.gsrc[0] = d.gsrc[1] = nullptr;
+   int i0, j0;          // absolute front row / column of the CTA's tile origin
+   int amax = GT_BM;    // rows of the CTA's tile (the right half of a diagonal tile has 64)
+   double acc[4][4][2];
+   if (mode == 2) {
+      // tile origin rounded down to an even row so the TMA source stays 16 B aligned
+      i0 = ((p0 + pw) & ~1) + local * GT_BM;
+      t.A = Lf + (size_t)p0 * ldl + i0;
+      t.lda = ldl;
+      t.arows = min(GT_BM, m - i0);
+      t.ldb = wld;
+      d.dbase = Lf; d.ldd = ldl; d.rmin = p0 + pw; d.lower = false; d.op = 2;
+      GemmPipe pipe;
+      gemm_pipe_init(pipe, smem);
+      const bool rows_ok = wm * 32 < t.arows;
+      for (int hh = (pw > GT_HN ? 1 : 0); hh >= 0; --hh) {
+         j0 = p0 + hh * GT_HN;
+         t.B = W + (size_t)fi * wld * wld + hh * GT_HN;   // slot fi of this launch's inverse buffer
+         t.brows = min(GT_HN, pw - hh * GT_HN);
+         t.K = min(pw, (hh + 1) * GT_HN);                  // W is lower triangular: k <= c
+         d.clo = j0; d.chi = j0 + t.brows;
+         const bool active = rows_ok && wn * 32 < t.brows;
+         gemm_tile_mainloop(pipe, t, active, acc);
+         if (active) gemm_tile_epilogue(d, i0, j0, acc);
+      }
+      return;
+   }
    if (mode >= 3) {
       // ---- indefinite path: operands are W = L*D (A side) and L (B side); the extent of the
       // update is read from the device-resident front state (nothing here is known to the host)
@@ -388,34 +554,19 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       if (tj >= TC) return;
       const int ti = tj + local;
       i0 = base + ti * GT_BM;
-      j0 = base + tj * GT_BN;
+      j0 = base + tj * GT_BN + half * GT_HN;
+      if (ti == tj && half) { i0 += GT_HN; amax = GT_HN; }      // right half of a diagonal tile: only its lower 64 rows
+      if (j0 >= cend || i0 >= m) return;
       t.A = Wf + (size_t)kbeg * ldl + i0;
       t.B = Lf + (size_t)kbeg * ldl + j0;
       t.lda = t.ldb = ldl;
-      t.arows = min(GT_BM, m - i0);
-      t.brows = min(GT_BN, m - j0);
       if (mode != 4) {
-         dbase = Lf; ldd = ldl; clo = first; chi = cend; rmin = 0; lower = true; op = 0;
-         t.prefetch = true;
+         d.dbase = Lf; d.ldd = ldl; d.clo = first; d.chi = cend; d.rmin = 0; d.lower = true; d.op = 0;
       } else {
          const int ldc = T.ldc[f];
-         dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
-         op = 1;      // children are extend-added afterwards (k_assemble_indef part 1)
-         t.prefetch = false;
+         d.dbase = T.C + T.coff[f] - (size_t)n * ldc - n; d.ldd = ldc; d.clo = n; d.chi = m; d.rmin = 0; d.lower = true;
+         d.op = 1;      // the other children are extend-added afterwards (k_assemble_indef part 1)
       }
-   } else if (mode == 2) {
-      // tile origin rounded down to an even row so the TMA source stays 16 B aligned
-      i0 = ((p0 + pw) & ~1) + local * GT_BM;
-      j0 = p0;
-      t.A = Lf + (size_t)p0 * ldl + i0;
-      t.lda = ldl;
-      t.arows = min(GT_BM, m - i0);
-      t.B = W + (size_t)fi * wld * wld;   // slot fi of this launch's inverse buffer
-      t.ldb = wld;
-      t.brows = pw;
-      t.K = pw;
-      dbase = Lf; ldd = ldl; clo = p0; chi = p0 + pw; rmin = p0 + pw; lower = false; op = 2;
-      t.prefetch = false;
    } else {
       const int base = (mode == 0) ? (p0 + pw) : (n & ~1);
       const int cend = (mode == 0) ? n : m;
@@ -426,121 +577,41 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       if (tj >= TC) return;
       const int ti = tj + local;
       i0 = base + ti * GT_BM;
-      j0 = base + tj * GT_BN;
+      j0 = base + tj * GT_BN + half * GT_HN;
+      if (ti == tj && half) { i0 += GT_HN; amax = GT_HN; }
+      if (j0 >= cend || i0 >= m) return;
       const int kbeg = (mode == 0) ? p0 : 0;
       t.K = (mode == 0) ? pw : n;
       t.A = Lf + (size_t)kbeg * ldl + i0;
       t.B = Lf + (size_t)kbeg * ldl + j0;
       t.lda = t.ldb = ldl;
-      t.arows = min(GT_BM, m - i0);
-      t.brows = min(GT_BN, m - j0);
       if (mode == 0) {
-         dbase = Lf; ldd = ldl; clo = p0 + pw; chi = n; rmin = 0; lower = true; op = 0;
-         t.prefetch = true;
+         d.dbase = Lf; d.ldd = ldl; d.clo = p0 + pw; d.chi = n; d.rmin = 0; d.lower = true; d.op = 0;
       } else {
          const int ldc = T.ldc[f];
-         dbase = T.C + T.coff[f] - (size_t)n * ldc - n; ldd = ldc; clo = n; chi = m; rmin = 0; lower = true;
-         op = 1;      // children are extend-added afterwards (k_assemble part 1)
-         t.prefetch = false;
+         d.dbase = T.C + T.coff[f] - (size_t)n * ldc - n; d.ldd = ldc; d.clo = n; d.chi = m; d.rmin = 0; d.lower = true;
+         d.op = 1;      // the other children are extend-added afterwards (k_assemble part 1)
       }
    }
-   t.dst = dbase + (size_t)j0 * ldd + i0;
-   t.ldd = ldd;
-   t.pf_c0 = max(0, clo - j0);
-   t.pf_c1 = min(GT_BN, chi - j0);
-   t.pf_lines = (min(GT_BM, m - i0) * 8 + 127) / 128;
-   t.gsrc[0] = t.gsrc[1] = nullptr;
-   if (op == 1 && T.fchild) {
+   t.arows = min(amax, m - i0);
+   t.brows = min(GT_HN, m - j0);
+   if (d.op == 1 && T.fchild) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
          const int fc = T.fchild[2 * f + s];
          if (fc < 0) continue;
-         t.gsrc[s] = T.C + T.coff[fc];
-         t.gld[s] = T.ldc[fc];
-         t.gmap[s] = T.pinv + T.pinvoff[2 * f + s];
-      }
-      t.g_r0 = i0 - n; t.g_c0 = j0 - n; t.g_k = m - n;
-   }
-   if (!gemm_tile_mainloop(t, smem)) return;
-
-   // ---- coalesced epilogue: warp w owns tile columns w*8 .. w*8+7, lanes stride the rows ----
-   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const bool interior = (i0 + GT_BM <= m) && (j0 >= clo) && (j0 + GT_BN <= chi) && (i0 >= j0 + GT_BN - 1 || !lower) &&
-                         (i0 >= rmin);
-   // Contribution block: fused extend-add.  The children's generated elements that the
-   // reference adds afterwards (assemble_contrib_block, src/kernels/assemble.hxx:343-517)
-   // are gathered here through the parent-row -> child-row maps, so the block is written
-   // once instead of written, re-read and re-written (8 + 8 B per entry instead of 8 + 24).
-   // All map entries a warp needs (4 row groups, its 8 columns) are loaded up front in one
-   // batch, and the gathers are predicated loads without branches, so that a warp keeps 16
-   // of them in flight instead of paying one memory latency per column.
-   const bool fused = t.gsrc[0] || t.gsrc[1];
-   int fir[2][4], fic[2][8];
-   if (fused) {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-#pragma unroll
-         for (int q = 0; q < 4; ++q) {
-            const int r = i0 + lane + 32 * q;
-            fir[s][q] = (t.gsrc[s] && r >= n && r < m) ? t.gmap[s][r - n] : -1;
-         }
-#pragma unroll
-         for (int u = 0; u < 8; ++u) {
-            const int c = j0 + warp * 8 + u;
-            fic[s][u] = (t.gsrc[s] && c >= n && c < m) ? t.gmap[s][c - n] : -1;
-         }
+         d.gsrc[s] = T.C + T.coff[fc];
+         d.gld[s] = T.ldc[fc];
+         d.gmap[s] = T.pinv + T.pinvoff[2 * f + s];
       }
    }
-#pragma unroll
-   for (int cq = 0; cq < 8; cq += 4) {
-      double v[4][4], d[4][4];
-      double* gp[4];
-      bool cok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-         const int ct = warp * 8 + cq + u;          // column inside the tile
-         const int c = j0 + ct;
-         cok[u] = interior || (c >= clo && c < chi);
-         gp[u] = dbase + (size_t)c * ldd + i0;
-#pragma unroll
-         for (int q = 0; q < 4; ++q) v[u][q] = smem[(size_t)ct * GT_LDC + lane + 32 * q];
-      }
-      if (fused) {
-#pragma unroll
-         for (int s = 0; s < 2; ++s) {
-            if (!t.gsrc[s]) continue;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-               const int ic = fic[s][cq + u];
-               const double* col = t.gsrc[s] + (size_t)max(ic, 0) * t.gld[s];
-#pragma unroll
-               for (int q = 0; q < 4; ++q) {
-                  const bool hit = ic >= 0 && fir[s][q] >= ic;      // maps are increasing: row >= col
-                  const double gv = hit ? col[fir[s][q]] : 0.0;
-                  v[u][q] -= gv;
-               }
-            }
-         }
-      }
-      if (op == 0) {
-#pragma unroll
-         for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-               const int r = i0 + lane + 32 * q;
-               const bool ok = interior || (cok[u] && r < m && r >= rmin && (!lower || r >= j0 + warp * 8 + cq + u));
-               d[u][q] = ok ? gp[u][lane + 32 * q] : 0.0;
-            }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-         for (int q = 0; q < 4; ++q) {
-            const int r = i0 + lane + 32 * q;
-            const bool ok = interior || (cok[u] && r < m && r >= rmin && (!lower || r >= j0 + warp * 8 + cq + u));
-            if (ok) gp[u][lane + 32 * q] = (op == 0) ? d[u][q] - v[u][q] : (op == 1 ? -v[u][q] : v[u][q]);
-         }
-   }
+   GemmPipe pipe;
+   gemm_pipe_init(pipe, smem);
+   // warps whose 32 x 32 block lies outside the tile or strictly above the diagonal do no math
+   const bool active = (wm * 32 < t.arows) && (wn * 32 < t.brows) && (i0 + wm * 32 + 31 >= j0 + wn * 32);
+   if (active) gemm_tile_prefetch(d, i0, j0);
+   gemm_tile_mainloop(pipe, t, active, acc);
+   if (active) gemm_tile_epilogue(d, i0, j0, acc);
 }
 
 // ---------------------------------------------------------------------------

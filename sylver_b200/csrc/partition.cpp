@@ -24,7 +24,8 @@ struct Mapper {
    const SymbolicTree& st;
    std::vector<double> wsub;      // flops of the subtree rooted at each front
    std::vector<double> wown;      // flops of the front itself
-   std::vector<double> load;      // per rank
+   std::vector<double> load;      // per rank: subtrees and fronts assigned so far
+   std::vector<double> expect;    // per rank: share of the multi-rank subtrees still to be mapped
    std::vector<int>& owner;
    std::vector<std::pair<int, std::pair<int, int>>> top;   // (front, rank group) above the cut, top-down
 
@@ -43,7 +44,7 @@ struct Mapper {
    int least_loaded(int r0, int r1) const {
       int best = r0;
       for (int r = r0 + 1; r < r1; ++r)
-         if (load[r] < load[best]) best = r;
+         if (load[r] + expect[r] < load[best] + expect[best]) best = r;
       return best;
    }
 
@@ -55,6 +56,11 @@ struct Mapper {
          const Item it = work.back();
          work.pop_back();
          const int nr = it.r1 - it.r0;
+         // the subtree below this front is being mapped now: its children re-enter `load`
+         // (whole subtrees) or `expect` (multi-rank children); the front itself stays expected
+         // until the fronts above the cut get their owners
+         if (it.f < st.nnodes)
+            for (int r = it.r0; r < it.r1; ++r) expect[r] -= (wsub[it.f] - wown[it.f]) / nr;
          std::vector<int> ch(st.child_list.begin() + st.child_ptr[it.f], st.child_list.begin() + st.child_ptr[it.f + 1]);
          if (ch.empty()) continue;
          std::stable_sort(ch.begin(), ch.end(), [&](int a, int b) { return wsub[a] > wsub[b]; });
@@ -91,11 +97,13 @@ struct Mapper {
             } else {
                top.push_back({c, {r, r + share[i]}});
                work.push_back({c, r, r + share[i]});
+               // work is a LIFO: this child's recursion has not run yet, so its ranks would look
+               // idle to the packing of the light children below -- charge its expected share
+               for (int q = r; q < r + share[i]; ++q) expect[q] += wsub[c] / share[i];
             }
             r += share[i];
          }
-         // the light children are packed afterwards (loads of the big ones are only known
-         // once their recursion bottomed out; pack onto currently least loaded rank)
+         // the light children are packed now, onto the rank with the least assigned + expected load
          for (int c : ch)
             if (std::find(big.begin(), big.end(), c) == big.end()) assign_subtree(c, least_loaded(it.r0, it.r1));
       }
@@ -123,13 +131,15 @@ void partition_tree(const SymbolicTree& st, int world, std::vector<int>& owner, 
       if (p < N) wsub[p] += wsub[f];
    }
    std::vector<int> own(N, -1);
-   Mapper mp{st, wsub, wown, std::vector<double>(world, 0.0), own, {}};
+   Mapper mp{st, wsub, wown, std::vector<double>(world, 0.0), std::vector<double>(world, 0.0), own, {}};
    mp.map_children(N, 0, world);       // children of the virtual root
    // fronts above the cut: bottom-up (reverse of discovery is not level order; sort by index,
    // children have smaller indices), least loaded rank of the group
    std::sort(mp.top.begin(), mp.top.end());
    for (auto& t : mp.top) {
-      const int r = mp.least_loaded(t.second.first, t.second.second);
+      const int g0 = t.second.first, g1 = t.second.second;
+      for (int q = g0; q < g1; ++q) mp.expect[q] -= wown[t.first] / (g1 - g0);
+      const int r = mp.least_loaded(g0, g1);
       own[t.first] = r;
       mp.load[r] += wown[t.first];
    }

@@ -182,6 +182,30 @@ def stokes_kkt(k: int):
     return n, ptr.astype(np.int64), (R + 1).astype(np.int32), V.astype(np.float64)
 
 
+def scale_down_some(n, ptr, row, val, frac: float, lo: float, hi: float):
+    """Symmetric scaling S A S with s_i = 10^(lo + (hi-lo) h2(i)) for the fraction `frac` of the
+    variables picked by a multiplicative hash of the index (seed-free), 1 elsewhere."""
+    i = np.arange(n, dtype=np.uint64)
+    h1 = (i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)
+    h2 = ((i * np.uint64(40503) + np.uint64(12345)) & np.uint64(0xFFFF)).astype(np.float64) / 65536.0
+    sc = np.where(h1 < np.uint64(int(0xFFFFFFFF * frac)), 10.0 ** (lo + (hi - lo) * h2), 1.0)
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    return val * sc[col] * sc[row - 1]
+
+
+KKTD_FRAC, KKTD_LO, KKTD_HI = 1.0 / 64, -6.0, -3.0
+
+
+def stokes_kkt_delays(k: int):
+    """BASELINE config 4 "with delayed pivots": the Stokes KKT system with a fraction of its
+    variables scaled down symmetrically by 10^-6 .. 10^-3 (the idea of the reference harness's
+    cause_delays, tests/common.hxx:162-179, applied to a sparse matrix): pivots that look
+    acceptable inside a front fail the a-posteriori threshold test and are delayed up the
+    tree.  Seed-free: the choice and the exponents are multiplicative hashes of the index."""
+    n, ptr, row, val = stokes_kkt(k)
+    return n, ptr, row, scale_down_some(n, ptr, row, val, KKTD_FRAC, KKTD_LO, KKTD_HI)
+
+
 # ----------------------------------------------------------------------------
 # dense fronts (config 2) -- reference generators tests/common.hxx:752-789
 # ----------------------------------------------------------------------------

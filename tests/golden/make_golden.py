@@ -46,18 +46,21 @@ def tree_case(kind, k, posdef):
     elif kind == "lap27":
         n, ptr, row, val = gen.laplacian_27pt(k)
         order = gen.nested_dissection_order(k)
+    elif kind == "kktd":
+        n, ptr, row, val = gen.stokes_kkt_delays(k)
+        order = gen.nested_dissection_order(k, dofs_per_cell=4)
     else:
         n, ptr, row, val = gen.stokes_kkt(k)
         order = gen.nested_dissection_order(k, dofs_per_cell=4)
     sym = osym_fast(n, ptr, row, order)
     ot = ref.OracleTree(sym)
-    ot.factor(val, posdef)
+    secs = ot.factor(val, posdef)
     b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
     x = ot.solve_original(b)
     st = ot.stats
     rec = dict(kind=kind, k=k, posdef=posdef, n=n, flag=st.flag, num_neg=st.num_neg, num_two=st.num_two,
                num_delay=st.num_delay, num_zero=st.num_zero, maxfront=st.maxfront,
-               bwderr=gen.backward_error(n, ptr, row, val, x, b))
+               bwderr=gen.backward_error(n, ptr, row, val, x, b), oracle_seconds=secs)
     ot.close()
     return rec
 
@@ -101,6 +104,23 @@ def numeric():
     json.dump(out, open(os.path.join(HERE, "numeric.json"), "w"), indent=1)
 
 
+def numeric_big():
+    """numeric_big.json: the BASELINE.json configurations themselves (or the largest stand-in the
+    CPU engine finishes in minutes here): config 2 (dense 8192 x 2048 APTP), config 3
+    (27-point Laplacian 100^3 posdef), config 4's matrix family at 40^3 with and without
+    delay-causing scaling, and 7-point LDL^T at 60^3.  Minutes of CPU time; run with `big`."""
+    out = {"trees": [], "dense": []}
+    path = os.path.join(HERE, "numeric_big.json")
+    for m, n, delays in ((8192, 2048, False), (8192, 2048, True)):
+        out["dense"].append(dense_case(m, n, delays))
+        print(out["dense"][-1], flush=True)
+    for kind, k, posdef in (("kktd", 12, False), ("kktd", 24, False), ("kkt", 40, False), ("kktd", 32, False),
+                            ("lap7", 60, False), ("lap27", 100, True), ("kktd", 40, False)):
+        out["trees"].append(tree_case(kind, k, posdef))
+        print(out["trees"][-1], flush=True)
+        json.dump(out, open(path, "w"), indent=1)
+
+
 def host_preprocessing():
     """preprocess.json: outputs of the restatements of SPRAL's Fortran pre-processing
     (oracle/scaling.py, oracle/matrix_clean.py) on fixed inputs, floats as hex strings: the three
@@ -135,6 +155,8 @@ def host_preprocessing():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         host_preprocessing()
+    elif len(sys.argv) > 1 and sys.argv[1] == "big":
+        numeric_big()
     else:
         symbolic()
         numeric()

@@ -84,3 +84,44 @@ def test_not_posdef_flag(lib):
     s.analyse(n, ptr, row, gen.nested_dissection_order(6))
     inf = s.factorize(val, posdef=True)
     assert inf.flag == -6
+
+
+def _illcond_spd(m, cond, kind, seed=7):
+    rng = np.random.default_rng(seed)
+    if kind == "graded":
+        # D B D with a well-conditioned SPD B and a graded diagonal: cond(A) ~ cond
+        b = rng.standard_normal((m, m))
+        b = b @ b.T / m + np.eye(m)
+        dd = cond ** (-0.5 * np.arange(m) / (m - 1))
+        return dd[:, None] * b * dd[None, :]
+    # Q diag(lambda) Q^T, eigenvalues log-spaced between 1 and 1/cond, no grading to exploit
+    q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    lam = cond ** (-np.arange(m) / (m - 1))
+    a = (q * lam) @ q.T
+    return 0.5 * (a + a.T)
+
+
+@pytest.mark.parametrize("kind,cond", [("graded", 1e12), ("spectrum", 1e8), ("spectrum", 1e11)])
+def test_dense_front_posdef_ill_conditioned(lib, oracle_ref, kind, cond):
+    """Stability guard of the panel solve (solve_block = dtrsm in the reference,
+    src/kernels/factor.hxx:95-138): on an ill-conditioned SPD front the factor must reproduce A
+    as well as the reference's backward-stable LAPACK/BLAS path does (10x rule) -- a panel solve
+    through an explicitly formed inverse alone loses a factor cond(L11)."""
+    sb.require_gpu()
+    m = 1024
+    a = _illcond_spd(m, cond, kind)
+    buf = np.asfortranarray(np.tril(a))
+    ret = lib.sylver_b200_factor_front_posdef(m, m, buf.ctypes.data, m, None, 128, None)
+    assert ret == m
+    Lo, _, info = oracle_ref.factor_front_posdef(a, m)
+    assert info == -1
+    L, Lo = np.tril(buf), np.tril(Lo)
+    # componentwise-scaled residual |A - L L^T|_ij / (|L||L|^T)_ij, the quantity Cholesky's
+    # backward error bound is stated in
+    def resid(F):
+        r = np.abs(a - F @ F.T)
+        s = np.abs(F) @ np.abs(F).T
+        return float((r / s).max())
+    r_gpu, r_ref = resid(L), resid(Lo)
+    print(f"\nill-conditioned SPD ({kind}, cond {cond:.0e}): residual gpu {r_gpu:.2e} reference {r_ref:.2e}")
+    assert r_gpu <= 10 * r_ref
