@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsylver_b200.so")
+# SYLVER_B200_LIB selects a kernel-variant build for A/B measurements (sylver_b200/build.py)
+LIB_PATH = os.environ.get("SYLVER_B200_LIB") or os.path.join(_HERE, "libsylver_b200.so")
 
 
 class Inform(C.Structure):

@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libsylver_b200.so")
+# A/B builds of kernel variants: SYLVER_B200_VARIANT=<tag> SYLVER_B200_DEFS="-DX=1 ..." builds
+# libsylver_b200_<tag>.so beside the product library (loaded with SYLVER_B200_LIB=<path>)
+VARIANT = os.environ.get("SYLVER_B200_VARIANT", "")
+OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libsylver_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 SOURCES = ["api.cpp", "analyse.cpp", "scaling.cpp", "clean.cpp", "ordering.cpp", "partition.cpp", "comm.cpp", "engine.cu", "engine_indef.cu", "aux.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -25,7 +28,8 @@ METIS_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(NVCC))
                          "libmetis_static.a")
 HAVE_METIS = os.path.exists(METIS_LIB)
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-          "-Xptxas", "-v" if os.environ.get("SYLVER_PTXAS_V") else "-O3"] + (["-DSYLVER_HAVE_METIS"] if HAVE_METIS else [])
+          "-Xptxas", "-v" if os.environ.get("SYLVER_PTXAS_V") else "-O3"] + (["-DSYLVER_HAVE_METIS"] if HAVE_METIS else []) \
+    + os.environ.get("SYLVER_B200_DEFS", "").split()
 
 
 def _deps(src: str):

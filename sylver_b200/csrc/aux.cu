@@ -5,6 +5,7 @@
 // tests/testing_factor_node_indef.hxx:44-460).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.hpp"
@@ -135,6 +136,12 @@ extern "C" double sylver_b200_bench_dmma(int kind, int n, int k, int iters) {
       DevTree T{dm, dn, dldl, dldc, dloff, dcoff, dcmo, dpar, dnch, nullptr, L, C};
       TileBatch b{dfr, dpre, 1};
       cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+      cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (getenv("SYLVER_B200_VERBOSE")) {
+         int nbk = 0;
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, k_gemm_batched, GT_THREADS, GT_SMEM_BYTES);
+         fprintf(stderr, "sylver_b200: k_gemm_batched resident CTAs per SM: %d\n", nbk);
+      }
       float best = 1e30f;
       for (int i = 0; i < iters + 1; ++i) {
          cudaEventRecord(e0);

@@ -1063,6 +1063,12 @@ static void set_kernel_attributes() {
    std::lock_guard<std::mutex> lk(mu);
    if (done) return;
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+   if (getenv("SYLVER_B200_VERBOSE")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm_batched, GT_THREADS, GT_SMEM_BYTES);
+      fprintf(stderr, "sylver_b200: k_gemm_batched resident CTAs per SM: %d\n", nb);
+   }
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<128>::SMEM));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<64>::SMEM));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<32>::SMEM));

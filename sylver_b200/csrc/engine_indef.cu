@@ -72,6 +72,7 @@ void indef_setup(NumericTree* nt) {
    // kernels.cuh kernels are per translation unit (static __global__): this TU's copy needs its
    // own opt-in to > 48 KB of dynamic shared memory
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
    nt->m.assign(N, 0); nt->n.assign(N, 0); nt->ldl.assign(N, 0); nt->loff.assign(N, 0);

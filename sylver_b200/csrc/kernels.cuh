@@ -164,8 +164,11 @@ constexpr int GT_LDA = 132;            // padded smem row strides (mod 16 == 4: 
 constexpr int GT_LDB = 68;
 constexpr int GT_STAGES = 4;
 constexpr int GT_LOOKAHEAD = 2;        // k-blocks in flight ahead of the one being consumed
-constexpr int GT_WARPS = 8;            // 4 (rows) x 2 (columns), 32 x 32 each
-constexpr int GT_THREADS = GT_WARPS * 32;
+constexpr int GT_WARPS = 8;            // consumer warps: 4 (rows) x 2 (columns), 32 x 32 each
+#ifndef GT_PRODUCER_WARP
+#define GT_PRODUCER_WARP 1             // 1: a ninth warp stages the operands (96-register cap); 0: the eight warps share the issue
+#endif
+constexpr int GT_THREADS = (GT_WARPS + GT_PRODUCER_WARP) * 32;
 constexpr size_t GT_STAGE_DOUBLES = (size_t)GT_KT * (GT_LDA + GT_LDB);
 constexpr size_t GT_SMEM_BYTES = GT_STAGES * GT_STAGE_DOUBLES * sizeof(double) + 2 * GT_STAGES * sizeof(uint64_t);
 static_assert(2 * (GT_SMEM_BYTES + 1024) <= 232448, "two CTAs per SM");
@@ -195,7 +198,7 @@ __device__ __forceinline__ void gemm_pipe_init(GemmPipe& p, double* smem) {
    p.gk = 0;
    if (threadIdx.x == 0) {
       for (int s = 0; s < GT_STAGES; ++s) {
-         mbar_init(&p.full[s], 1);
+         mbar_init(&p.full[s], GT_PRODUCER_WARP ? 1 : GT_WARPS);
          mbar_init(&p.empty[s], GT_WARPS);
       }
       mbar_fence_init();
@@ -203,8 +206,11 @@ __device__ __forceinline__ void gemm_pipe_init(GemmPipe& p, double* smem) {
    __syncthreads();
 }
 
-// warp 0: stage k-block kb of the tile (lane l < 16 copies A column l, lane 16 + l B column l)
-__device__ __forceinline__ void gemm_issue_block(const GemmPipe& p, const GemmTile& t, int kb, bool share, int lane) {
+// Stages k-block kb of the tile.  Producer-warp build: called by the ninth warp, lane l < 16
+// copies A column l, lane 16 + l B column l.  Shared-issue build: called by every consumer warp,
+// warp w copies k-columns 2w and 2w + 1 (lanes 0/1 the A columns, lanes 2/3 the B columns).
+__device__ __forceinline__ void gemm_issue_block(const GemmPipe& p, const GemmTile& t, int kb, bool share, int warp,
+                                                 int lane) {
    const int G = p.gk + kb;
    const int s = G % GT_STAGES;
    if (G >= GT_STAGES) mbar_wait(&p.empty[s], ((G / GT_STAGES) - 1) & 1);
@@ -212,24 +218,46 @@ __device__ __forceinline__ void gemm_issue_block(const GemmPipe& p, const GemmTi
    const int kv = min(GT_KT, t.K - k0);           // valid k-columns in this stage
    double* As = p.smem + s * GT_STAGE_DOUBLES;
    double* Bs = As + GT_KT * GT_LDA;
-   const int kc = lane & 15;
-   const bool isB = lane >= 16;
    const uint32_t abytes = (uint32_t)(((t.arows + 1) & ~1) * sizeof(double));
    const uint32_t bbytes = (uint32_t)(((t.brows + 1) & ~1) * sizeof(double));
-   if (kc >= kv && kc < ((kv + 3) & ~3)) {
+   const int kz = (kv + 3) & ~3;
+#if GT_PRODUCER_WARP
+   const int kc = lane & 15;
+   const bool isB = lane >= 16;
+   const bool mine = lane < 32;
+   if (kc >= kv && kc < kz) {
       // zero-fill the tail of a partial k-group (generic proxy; ordered by the arrive below)
       if (!isB) {
-         double* dst = As + kc * GT_LDA;
-         for (int r = 0; r < GT_BM; ++r) dst[r] = 0.0;
+         for (int r = 0; r < GT_BM; ++r) As[kc * GT_LDA + r] = 0.0;
       } else if (!share) {
-         double* dst = Bs + kc * GT_LDB;
-         for (int r = 0; r < GT_HN; ++r) dst[r] = 0.0;
+         for (int r = 0; r < GT_HN; ++r) Bs[kc * GT_LDB + r] = 0.0;
       }
    }
    __syncwarp();
    if (lane == 0) mbar_expect_tx(&p.full[s], kv * (abytes + (share ? 0u : bbytes)));
+   (void)warp;
+#else
+   const int kc = 2 * warp + (lane & 1);
+   const bool isB = (lane & 2) != 0;
+   const bool mine = lane < 4;
+   if (kv < kz && 2 * warp + 1 >= kv && 2 * warp < kz) {
+      for (int c = max(kv, 2 * warp); c < min(kz, 2 * warp + 2); ++c) {
+         for (int r = lane; r < GT_BM; r += 32) As[c * GT_LDA + r] = 0.0;
+         if (!share)
+            for (int r = lane; r < GT_HN; r += 32) Bs[c * GT_LDB + r] = 0.0;
+      }
+   }
    __syncwarp();
-   if (kc < kv) {
+   if (lane == 0) {
+      // every warp arrives (its zero fill is ordered before the consumers' reads); warp 0 posts
+      // the byte count of the whole stage -- copies of other warps may complete first, the
+      // transaction count then goes negative for a moment
+      if (warp == 0) mbar_expect_tx(&p.full[s], kv * (abytes + (share ? 0u : bbytes)));
+      else mbar_arrive(&p.full[s]);
+   }
+#endif
+   __syncwarp();
+   if (mine && kc < kv) {
       if (!isB)
          tma_bulk_g2s(As + kc * GT_LDA, t.A + (size_t)(k0 + kc) * t.lda, abytes, &p.full[s]);
       else if (!share)
@@ -239,22 +267,33 @@ __device__ __forceinline__ void gemm_issue_block(const GemmPipe& p, const GemmTi
 
 // Accumulates the product tile: acc[ic][jr][h] = sum_k B[col][k] A[row][k] with
 //   col = wn*32 + ic*8 + g,  row = wm*32 + jr*8 + 2*tq + h      (lane = 4*g + tq).
-// `active` warps compute; the others only keep the pipeline's barriers moving.
+// `active` warps compute; the others only keep the pipeline moving.
 __device__ __forceinline__ void gemm_tile_mainloop(GemmPipe& p, const GemmTile& t, bool active, double (&acc)[4][4][2]) {
    const int warp = threadIdx.x >> 5;
    const int lane = threadIdx.x & 31;
    const int nk = (t.K + GT_KT - 1) / GT_KT;
    const bool share = (t.A == t.B) && (t.lda == t.ldb);   // diagonal tile: the columns are rows of A
+#if GT_PRODUCER_WARP
+   if (warp == GT_WARPS) {
+      // producer warp: runs ahead of the consumers by up to GT_STAGES k-blocks
+      for (int kb = 0; kb < nk; ++kb) gemm_issue_block(p, t, kb, share, warp, lane);
+      p.gk += nk;
+      return;
+   }
+#endif
    const int wm = warp & 3, wn = warp >> 2;
    const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-   if (warp == 0)
-      for (int kb = 0; kb < min(nk, GT_LOOKAHEAD); ++kb) gemm_issue_block(p, t, kb, share, lane);
+#if !GT_PRODUCER_WARP
+   for (int kb = 0; kb < min(nk, GT_LOOKAHEAD); ++kb) gemm_issue_block(p, t, kb, share, warp, lane);
+#endif
    for (int kb = 0; kb < nk; ++kb) {
-      if (warp == 0 && kb + GT_LOOKAHEAD < nk) gemm_issue_block(p, t, kb + GT_LOOKAHEAD, share, lane);
+#if !GT_PRODUCER_WARP
+      if (kb + GT_LOOKAHEAD < nk) gemm_issue_block(p, t, kb + GT_LOOKAHEAD, share, warp, lane);
+#endif
       const int G = p.gk + kb;
       const int s = G % GT_STAGES;
       mbar_wait(&p.full[s], (G / GT_STAGES) & 1);
@@ -526,7 +565,7 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
          t.brows = min(GT_HN, pw - hh * GT_HN);
          t.K = min(pw, (hh + 1) * GT_HN);                  // W is lower triangular: k <= c
          d.clo = j0; d.chi = j0 + t.brows;
-         const bool active = rows_ok && wn * 32 < t.brows;
+         const bool active = warp < GT_WARPS && rows_ok && wn * 32 < t.brows;
          gemm_tile_mainloop(pipe, t, active, acc);
          if (active) gemm_tile_epilogue(d, i0, j0, acc);
       }
@@ -608,7 +647,7 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    GemmPipe pipe;
    gemm_pipe_init(pipe, smem);
    // warps whose 32 x 32 block lies outside the tile or strictly above the diagonal do no math
-   const bool active = (wm * 32 < t.arows) && (wn * 32 < t.brows) && (i0 + wm * 32 + 31 >= j0 + wn * 32);
+   const bool active = warp < GT_WARPS && (wm * 32 < t.arows) && (wn * 32 < t.brows) && (i0 + wm * 32 + 31 >= j0 + wn * 32);
    if (active) gemm_tile_prefetch(d, i0, j0);
    gemm_tile_mainloop(pipe, t, active, acc);
    if (active) gemm_tile_epilogue(d, i0, j0, acc);
