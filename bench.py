@@ -19,9 +19,15 @@ num_flops (spral/src/core_analyse.f90:880-892).
   roofline : the DMMA tile kernel (k_gemm_batched: trsm + update + contribution),
           algorithmic flops / CUDA-event time, against the FP64 DMMA issue peak
           measured in the same run (MEASURED_PEAKS.json has no FP64 figure)
-  cpu_baseline / --impl reference : the SSIDS CPU engine (oracle/_ref, the code
-          SyLVER delegates subtrees to) on the host cores, on a bounded sample
-          (27-point Laplacian on a smaller grid) -- the full StarPU build cannot be
+  hbm_rooflines : achieved GB/s of the bandwidth-bound kernels (extend-add, A scatter) against
+          MEASURED_PEAKS.json's HBM figure, algorithmic bytes of SURVEY.md 8d
+  secondary : the other BASELINE configurations, same engine, same run: the dense APTP front
+          (config 2), LDL^T and delayed-pivot KKT trees (configs 4/5 family), on N GPUs
+  cpu_baseline : the reference's CPU engine (oracle/_ref = SPRAL/SSIDS compiled from
+          /root/reference) on a bounded sample OF THE SAME WORKLOAD: a prefix of lap27_100's
+          own assembly tree in postorder (a forest of complete subtrees)
+  --impl reference : the same CPU engine on lap27_100 ITSELF, every step a full factorization,
+          the step count capped by a time budget (printed) -- the full StarPU build cannot be
           produced here.
 """
 from __future__ import annotations
@@ -51,8 +57,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=100, help="grid side of the 27-point Laplacian")
-    ap.add_argument("--sample-grid", type=int, default=56, help="grid side of the CPU sample (56^3: ~4 s of CPU work per step)")
+    ap.add_argument("--cpu-sample-frac", type=float, default=0.12,
+                    help="cpu_baseline: fraction of the workload's flops in the postorder-prefix sample")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: no new CPU step is started after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--secondary-budget-s", type=float, default=300.0)
     return ap.parse_args()
 
 
@@ -63,59 +74,109 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-# ----------------------------------------------------------------------------
-# reference arm / cpu baseline: SSIDS CPU engine on a bounded sample
-# ----------------------------------------------------------------------------
-def run_reference_sample(grid: int, steps: int, warmup: int):
-    cores = host_cores()
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
-    import numpy as np
-    import sylver_b200 as sb
+def workload(grid):
     from sylver_b200 import gen
-    from oracle import ref
-    if not ref.available():
-        return None
     n, ptr, row, val = gen.laplacian_27pt(grid)
     order = gen.nested_dissection_order(grid)
-    s = sb.Solver()
-    inf = s.analyse(n, ptr, row, order)        # host-only symbolic analysis (shared input)
-    sym = s.symbolic()
-    ot = ref.OracleTree(sym)
-    for _ in range(max(0, warmup)):
-        ot.factor(val, True)
-    t = 0.0
-    for _ in range(steps):
-        t += ot.factor(val, True)
-    assert ot.stats.flag == 0
-    gf = steps * inf.num_flops / t / 1e9
-    sample = (f"27-point Laplacian {grid}^3 (n={n}, {inf.num_flops:.3e} flops/step), posdef, "
-              f"SSIDS CPU engine (task-sequential, OpenBLAS {cores} threads), {steps} steps in {t:.2f} s")
-    ot.close()
-    return dict(value=gf, cores=cores, sample=sample, seconds=t, flops=inf.num_flops)
+    return n, ptr, row, val, order
+
+
+def config_of(grid, n, ptr, num_flops):
+    """Identical in both arms (the driver compares it)."""
+    return {"workload": f"lap27_{grid}", "n": int(n), "nnz_lower": int(ptr[-1] - 1), "num_flops": int(num_flops),
+            "order": "geometric nested dissection (input)", "nemin": 32}
+
+
+# ----------------------------------------------------------------------------
+# reference CPU engine (oracle/_ref): --impl reference and cpu_baseline
+# ----------------------------------------------------------------------------
+def cpu_engine_setup():
+    """Task-parallel SSIDS (OpenMP tasks on all host cores, sequential BLAS) when liboracle_omp.so
+    travelled with the snapshot, else task-sequential SSIDS with threaded OpenBLAS.  Must run
+    before the oracle library (and its OpenMP/OpenBLAS runtimes) is loaded."""
+    cores = host_cores()
+    from oracle import ref
+    if os.path.exists(ref.OMP_LIB_PATH):
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        if ref.select_task_parallel():
+            return ref, cores, (f"SSIDS CPU engine, OpenMP task-parallel on {cores} threads (sequential BLAS; the reference's "
+                                f"`default(none)` task clauses patched to `default(shared)` at build time for gcc 13, oracle/Makefile)")
+    os.environ["OPENBLAS_NUM_THREADS"] = str(cores)
+    return ref, cores, f"SSIDS CPU engine, task-sequential, OpenBLAS {cores} threads"
+
+
+def node_flops(sym):
+    import numpy as np
+    ncol = np.diff(sym["sptr"]).astype(np.float64)
+    nrow = np.diff(sym["rptr"]).astype(np.float64)
+    mm = nrow - ncol
+    # sum_{j=1..ncol} (mm + j)^2
+    return ncol * mm * mm + mm * ncol * (ncol + 1) + ncol * (ncol + 1) * (2 * ncol + 1) / 6.0
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = run_reference_sample(a.sample_grid, a.steps, min(a.warmup, 1))
-    if r is None:
+    ref, cores, how = cpu_engine_setup()
+    if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle.so missing (build needs /root/reference)"}))
         return
+    import sylver_b200 as sb
+    n, ptr, row, val, order = workload(a.grid)
+    s = sb.Solver()
+    inf = s.analyse(n, ptr, row, order)        # host-only symbolic analysis (shared input of both arms)
+    sym = s.symbolic()
+    num_flops = int(inf.num_flops)
+    ot = ref.OracleTree(sym)
+    t, done = 0.0, 0
+    w0 = time.perf_counter()
+    while done < a.steps and (done == 0 or time.perf_counter() - w0 + t / done < a.ref_budget_s):
+        t += ot.factor(val, True)
+        done += 1
+    assert ot.stats.flag == 0
+    ot.close()
+    gf = done * num_flops / t / 1e9
+    sample = (f"lap27_{a.grid} itself, {done} full factorization(s) in {t:.1f} s (requested {a.steps} steps, no warm-up: "
+              f"no new step is started once the next one would pass {a.ref_budget_s:.0f} s); {how}")
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / a.steps,
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": done, "warmup": 0, "steps_requested": a.steps, "ms_per_step": 1e3 * t / done,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "lap27_100 (bounded CPU sample: lap27_%d)" % a.sample_grid,
-                   "note": "reference CPU path = SPRAL/SSIDS CPU engine built from /root/reference "
-                           "(full SyLVER/StarPU build is not producible: no Fortran, StarPU, hwloc, METIS)"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
-                         "sample": r["sample"]},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "data": "synthetic", "config": config_of(a.grid, n, ptr, num_flops),
+        "note": "reference CPU path = SPRAL/SSIDS CPU engine built from /root/reference (the code SyLVER delegates "
+                "subtrees to); the full SyLVER/StarPU build is not producible: no Fortran, StarPU, hwloc, METIS",
+        "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def cpu_sample(a, sym, val, num_flops):
+    """cpu_baseline: the CPU engine on the first nodes of lap27_100's own assembly tree (postorder
+    prefix = complete subtrees) holding about --cpu-sample-frac of the flops."""
+    import numpy as np
+    ref, cores, how = cpu_engine_setup()
+    if not ref.available():
+        return None
+    fl = np.cumsum(node_flops(sym))
+    last = int(np.searchsorted(fl, a.cpu_sample_frac * fl[-1]))
+    last = max(1, min(last, sym["nnodes"]))
+    ot = ref.OracleTree(sym, last_node=last)
+    ot.factor(val, True)                 # warm-up (page faults of the factor storage)
+    t = ot.factor(val, True)
+    flag = ot.stats.flag
+    ot.close()
+    if flag != 0:
+        return None
+    sf = float(fl[last - 1])
+    return {"value": sf / t / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": (f"first {last} of {sym['nnodes']} fronts of lap27_{a.grid}'s assembly tree in postorder (complete "
+                       f"subtrees, {sf:.3e} flops = {100 * sf / fl[-1]:.0f}% of the factorization), 1 warm-up + 1 timed "
+                       f"factorization in {t:.1f} s; {how}")}
 
 
 # ----------------------------------------------------------------------------
@@ -170,6 +231,94 @@ class ClockSampler:
                 "power_w_max": max(power), "samples": len(sm)}
 
 
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6445.0, "fallback 6445 GB/s (MEASURED_PEAKS.json absent on this box)"
+
+
+# ----------------------------------------------------------------------------
+# secondary workloads (the other BASELINE configurations)
+# ----------------------------------------------------------------------------
+def secondary_tree(sb, gen, np, dist, name, n, ptr, row, val, order, posdef, reps, golden=None):
+    s = sb.Solver(ngpu=1)
+    t0 = time.perf_counter()
+    inf = s.analyse(n, ptr, row, order)
+    t_an = time.perf_counter() - t0
+    assert inf.flag == 0, inf.flag
+    flops = int(inf.num_flops)
+    best = None
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        w0 = time.perf_counter()
+        inf = s.factorize(val, posdef=posdef)
+        if dist is not None:
+            dist.barrier()
+        w = time.perf_counter() - w0
+        dev = s.timings()["device_s"]
+        sec = w if dist is not None else dev       # multi-GPU: wall between barriers (max over ranks)
+        best = sec if best is None else min(best, sec)
+    rec = {"workload": name, "n": int(n), "num_flops": flops, "posdef": posdef, "seconds": best,
+           "tflops": flops / best / 1e12, "flag": int(inf.flag), "num_neg": int(inf.num_neg), "num_two": int(inf.num_two),
+           "num_delay": int(inf.num_delay), "maxfront": int(inf.maxfront), "analyse_s": t_an,
+           "split_fronts": (s.split_info() or (0, 0, 0))[0],
+           "timed": "wall clock between barriers, min of %d" % reps if dist is not None else "CUDA events (device), min of %d" % reps}
+    b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
+    x = s.solve(b)
+    rec["bwderr"] = gen.backward_error(n, ptr, row, val, x, b)
+    if golden is not None:
+        rec["reference_num_neg"] = golden
+        rec["inertia_matches_reference"] = bool(int(inf.num_neg) == golden)
+    s.free()
+    return rec
+
+
+def run_secondaries(a, sb, gen, np, dist, rank, world, out):
+    """Appends records to `out` (rank 0 reports them).  Order: cheapest first."""
+    try:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "numeric_big.json")))
+    except Exception:
+        golden = {"trees": [], "dense": []}
+
+    def gold(kind, k):
+        for r in golden["trees"]:
+            if r["kind"] == kind and r["k"] == k:
+                return int(r["num_neg"])
+        return None
+
+    if world == 1:
+        # config 2: single dense APTP front 8192 x 2048 (tests/testing_factor_node_indef.hxx shape)
+        m, ncol = 8192, 2048
+        A = gen.dense_sym_indef(m, rng=gen.GlibcRand(1))
+        flops = float(sum((m - ncol + j) ** 2 for j in range(1, ncol + 1)))
+        best, res = None, None
+        for _ in range(3):
+            res = sb.factor_front_indef(A, ncol)
+            best = res["ms"] if best is None else min(best, res["ms"])
+        gd = next((r for r in golden["dense"] if not r["delays"] and r["m"] == m), None)
+        out.append({"workload": "config 2: dense front 8192 x 2048, APTP LDL^T (u = 0.01)", "ms": best,
+                    "tflops": flops / (best * 1e-3) / 1e12, "num_flops": flops, "nelim": int(res["nelim"]),
+                    "num_neg": int(res["stats"].num_neg), "num_two": int(res["stats"].num_two),
+                    "num_delay": int(res["stats"].num_delay),
+                    "reference_num_neg": gd["num_neg"] if gd else None,
+                    "inertia_matches_reference": bool(gd and gd["num_neg"] == int(res["stats"].num_neg)),
+                    "parity_test": "tests/test_gpu_configs.py::test_config2_dense_8192x2048_aptp (bwderr, |l| <= 1/u, Sylvester)"})
+        del A
+        n, ptr, row, val = gen.laplacian_7pt(100)
+        out.append(secondary_tree(sb, gen, np, None, "config 5 family: 7-point Laplacian 100^3 LDL^T (APTP), 1 GPU", n, ptr, row, val,
+                                  gen.nested_dissection_order(100), False, 3, 0))
+    n, ptr, row, val = gen.stokes_kkt_delays(40)
+    out.append(secondary_tree(sb, gen, np, dist, f"config 4 family: Stokes KKT 40^3 (n = 256 000) with delay-causing scaling, {world} GPU(s)",
+                              n, ptr, row, val, gen.nested_dissection_order(40, dofs_per_cell=4), False, 2, gold("kktd", 40)))
+    if world > 1:
+        # the north-star target problem: 7-point Laplacian 150^3 LDL^T (n = 3 375 000, 7.5e13 flops)
+        n, ptr, row, val = gen.laplacian_7pt(150)
+        out.append(secondary_tree(sb, gen, np, dist, f"north-star target: 7-point Laplacian 150^3 LDL^T (APTP), {world} GPUs",
+                                  n, ptr, row, val, gen.nested_dissection_order(150), False, 2, 0))
+
+
 # ----------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------
@@ -202,8 +351,7 @@ def ours(a):
             dist.barrier()
 
     # ---- workload (synthetic), analysis excluded from timing ----
-    n, ptr, row, val = gen.laplacian_27pt(a.grid)
-    order = gen.nested_dissection_order(a.grid)
+    n, ptr, row, val, order = workload(a.grid)
     stream = torch.cuda.Stream()
     L.sylver_b200_set_stream.argtypes = [C.c_void_p, C.c_int]
     L.sylver_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
@@ -213,6 +361,7 @@ def ours(a):
     t_analyse = time.perf_counter() - t0
     assert inf.flag == 0, inf.flag
     num_flops = int(inf.num_flops)
+    sym = s.symbolic() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     d_val = torch.from_numpy(val).to("cuda")
     h_val = torch.from_numpy(val).pin_memory()
     dptr = int(d_val.data_ptr())
@@ -252,7 +401,8 @@ def ours(a):
         torch.cuda.synchronize(); barrier()
         dt_e2e = max(f0.elapsed_time(f1) * 1e-3, time.perf_counter() - w0)
 
-    # parity gate on the very factors that were timed (backward error, oracle-free property)
+    # parity gate on the very factors that were timed (backward error; the golden record of the
+    # reference engine on this input is tests/golden/numeric_big.json, checked by tests/test_gpu_configs.py)
     x0 = np.ones(n)
     b = gen.sym_matvec(n, ptr, row, val, x0)
     x = s.solve(b)
@@ -263,82 +413,122 @@ def ours(a):
         t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dt_e2e = float(t[0]), float(t[1])
+    ms_step = 1e3 * dt / a.steps
 
-    # ---- roofline of the dominant kernel: profiled (un-graphed) pass with CUDA events ----
-    roof = None
-    breakdown = None
-    if True:        # collective at N > 1: every rank profiles its own share, rank 0 reports
-        s.free()
-        os.environ["SYLVER_B200_PROFILE"] = "1"
-        sp = sb.Solver(ngpu=1)
-        sp.analyse(n, ptr, row, order)
-        with torch.cuda.stream(stream):
-            sp.factorize(dptr, posdef=True)
-            sp.factorize(dptr, posdef=True)
-            torch.cuda.synchronize()
-        prof = (C.c_double * 32)()
-        L.sylver_b200_numeric_tree_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-        nk = L.sylver_b200_numeric_tree_profile(L.sylver_b200_fkeep_tree(sp.fkeep), prof, 32)
-        os.environ.pop("SYLVER_B200_PROFILE")
-        ms = {KNAMES[i]: prof[3 * i] for i in range(nk)}
-        nl = {KNAMES[i]: int(prof[3 * i + 1]) for i in range(nk)}
-        fl = {KNAMES[i]: prof[3 * i + 2] for i in range(nk)}
-        tot_ms = sum(ms.values())
-        g_ms = ms["trsm"] + ms["update"] + ms["contrib"]
-        g_fl = fl["trsm"] + fl["update"] + fl["contrib"]
-        g_nl = nl["trsm"] + nl["update"] + nl["contrib"]
-        peak = L.sylver_b200_bench_dmma(0, 0, 0, 5)
-        achieved = g_fl / (g_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("k_gemm_batched_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"bound": "tensor", "kernel": "k_gemm_batched (DMMA.8x8x4 tiles: trsm+update+contrib)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "FP64 DMMA issue peak measured in this run by sylver_b200_bench_dmma(0) "
-                               "(MEASURED_PEAKS.json has no FP64 figure)",
-                "flops_per_launch": g_fl / max(g_nl, 1), "avg_launch_ms": g_ms / max(g_nl, 1),
-                "launches": g_nl, "share_of_step": g_ms / tot_ms, "traffic": traffic}
-        breakdown = {k: {"ms": round(ms[k], 3), "launches": nl[k]} for k in ms}
-        if world > 1:
-            roof["note"] = "rank 0's share of the tree (fronts mapped to GPU 0)"
-        sp.free()
+    # ---- rooflines: profiled (un-graphed) pass, CUDA events around every launch on its stream ----
+    s.free()
+    os.environ["SYLVER_B200_PROFILE"] = "1"
+    sp = sb.Solver(ngpu=1)
+    sp.analyse(n, ptr, row, order)
+    with torch.cuda.stream(stream):
+        sp.factorize(dptr, posdef=True)
+        sp.factorize(dptr, posdef=True)
+        torch.cuda.synchronize()
+    prof = (C.c_double * 32)()
+    nk = L.sylver_b200_numeric_tree_profile(L.sylver_b200_fkeep_tree(sp.fkeep), prof, 32)
+    os.environ.pop("SYLVER_B200_PROFILE")
+    ms = {KNAMES[i]: prof[3 * i] for i in range(nk)}
+    nl = {KNAMES[i]: int(prof[3 * i + 1]) for i in range(nk)}
+    fl = {KNAMES[i]: prof[3 * i + 2] for i in range(nk)}
+    g_ms = ms["trsm"] + ms["update"] + ms["contrib"]
+    g_fl = fl["trsm"] + fl["update"] + fl["contrib"]
+    g_nl = nl["trsm"] + nl["update"] + nl["contrib"]
+    peak = L.sylver_b200_bench_dmma(0, 0, 0, 5)
+    achieved = g_fl / (g_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_gemm_batched_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = {"bound": "tensor", "kernel": "k_gemm_batched (DMMA.8x8x4 tiles: trsm+update+contrib)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "FP64 DMMA issue peak measured in this run by sylver_b200_bench_dmma(0) "
+                           "(MEASURED_PEAKS.json has no FP64 figure)",
+            "flops_per_launch": g_fl / max(g_nl, 1), "avg_launch_ms": g_ms / max(g_nl, 1),
+            "launches": g_nl,
+            "share_of_step": g_ms / ms_step,
+            "share_note": "kernel time of the profiled (un-graphed, event-bracketed) pass / the timed step",
+            "per_mode": {k: {"tflops": fl[k] / max(ms[k], 1e-9) / 1e9, "frac": fl[k] / max(ms[k], 1e-9) / 1e9 / peak}
+                         for k in ("trsm", "update", "contrib")},
+            "traffic": traffic}
+    hbm_peak, hbm_src = measured_hbm_peak()
+    hbm = {}
+    for k, kern, what in (("assemble", "k_assemble", "extend-add: 8 B source + 16 B destination RMW + 4 B index per contributed entry"),
+                          ("scatter", "k_scatter_a", "A scatter: 8 B value + 16 B (src,dest) map pair + 8 B store per entry")):
+        if ms.get(k, 0) > 0:
+            gbs = fl[k] / (ms[k] * 1e-3) / 1e9
+            hbm[kern] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_step": fl[k], "ms_per_step": ms[k], "launches": nl[k],
+                         "share_of_step": ms[k] / ms_step, "bytes": what}
+    breakdown = {k: {"ms": round(ms[k], 3), "launches": nl[k]} for k in ms}
+    if world > 1:
+        roof["note"] = "rank 0's share of the tree (fronts mapped to GPU 0)"
+    sp.free()
+
+    # ---- secondary workloads, under a watchdog: a stuck collective must not cost the headline ----
+    L.sylver_b200_set_stream(None, 0)
+    secondary = []
+    state = {"done": False, "line": None}
+
+    def emit(status):
+        if rank == 0 and state["line"] is not None:
+            state["line"]["secondary"] = secondary
+            state["line"]["secondary_status"] = status
+            print(json.dumps(state["line"]), flush=True)
+
+    def watchdog():
+        deadline = time.time() + a.secondary_budget_s
+        while time.time() < deadline:
+            if state["done"]:
+                return
+            time.sleep(0.5)
+        emit("watchdog: secondary workloads exceeded %.0f s, records so far kept" % a.secondary_budget_s)
+        os._exit(0)
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = run_reference_sample(a.sample_grid, 3, 1)
-        if r is not None:
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
-                   "sample": r["sample"]}
-
     if rank == 0:
-        # one factorization is spread over all GPUs (tree partition): total work is fixed
         value = a.steps * num_flops / dt / 1e9
         e2e = a.steps * num_flops / dt_e2e / 1e9
-        line = {
+        cfg = config_of(a.grid, n, ptr, num_flops)
+        cfg.update({"parallelism": "1 GPU" if world == 1 else
+                    f"assembly tree partitioned over {world} GPUs (proportional mapping), contribution "
+                    f"blocks of cross-GPU edges by NCCL send/recv; {split[0]} top-of-tree fronts split "
+                    f"block-column-cyclic over their rank group (panel ncclBroadcast)",
+                    "l2": "factor+contribution arenas (>20 GB) far exceed the 126 MB L2; no flush needed",
+                    "analyse_s": t_analyse, "bwderr": bwderr})
+        state["line"] = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"lap27_{a.grid}", "n": n, "nnz_lower": int(ptr[-1] - 1),
-                       "num_flops": num_flops, "order": "geometric nested dissection (input)",
-                       "nemin": 32, "parallelism": "1 GPU" if world == 1 else
-                       f"assembly tree partitioned over {world} GPUs (proportional mapping), contribution "
-                       f"blocks of cross-GPU edges by NCCL send/recv; {split[0]} top-of-tree fronts split "
-                       f"block-column-cyclic over their rank group (panel ncclBroadcast)",
-                       "l2": "factor+contribution arenas (>20 GB) far exceed the 126 MB L2; no flush needed",
-                       "analyse_s": t_analyse, "bwderr": bwderr},
+            "config": cfg,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(val.nbytes),
                     "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * dt_e2e / a.steps},
             "gpu_launches": int(launches_per_step) * a.steps,
             "clocks": clk,
             "roofline": roof,
+            "hbm_rooflines": hbm,
             "kernel_breakdown_ms": breakdown,
-            "cpu_baseline": cpu,
+            "cpu_baseline": None,
         }
-        print(json.dumps(line))
+    if not a.no_secondary:
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            run_secondaries(a, sb, gen, np, dist, rank, world, secondary)
+            status = "ok"
+        except Exception as e:      # keep the headline
+            status = "error: %r" % (e,)
+    else:
+        status = "skipped (--no-secondary)"
+    state["done"] = True
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            cpu = cpu_sample(a, sym, val, num_flops)
+        except Exception as e:
+            cpu = {"error": repr(e)}
+        state["line"]["cpu_baseline"] = cpu
+    emit(status)
     if dist is not None:
         dist.barrier()
         L.sylver_b200_comm_finalize()

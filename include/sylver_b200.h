@@ -277,6 +277,8 @@ int sylver_b200_numeric_tree_split_info(void const *tree, int *out3);
  * scatter, zero, assemble, potrf|pivot, trsm|tpp, update, contrib.  Returns the number of
  * classes (0 when profiling is off). */
 int sylver_b200_numeric_tree_profile(void const *tree, double *out, int cap);
+/* Same run, per tree level: out[level * 7 + class] = milliseconds.  Returns the number of levels. */
+int sylver_b200_numeric_tree_profile_levels(void const *tree, double *out, int cap);
 /* Device bytes held by a numeric tree (total; factor and contribution arenas separately). */
 long sylver_b200_numeric_tree_bytes(void const *tree, long *factor_bytes, long *contrib_bytes);
 /* Issue all work of subsequently created numeric trees on the caller's CUDA stream

@@ -55,8 +55,23 @@ def default_options() -> CpuFactorOptions:
 _lib = None
 
 
+OMP_LIB_PATH = os.path.join(_HERE, "_ref", "liboracle_omp.so")
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
+
+
+def select_task_parallel() -> bool:
+    """CPU-baseline timing only: load liboracle_omp.so (the same sources built with OpenMP tasks,
+    `make -C oracle omp`) instead of the sequential library.  Must be called before the first
+    lib(); the caller sets OMP_NUM_THREADS / OPENBLAS_NUM_THREADS.  Returns False if that build
+    is absent (the sequential library is used then)."""
+    global LIB_PATH
+    if _lib is not None or not os.path.exists(OMP_LIB_PATH):
+        return False
+    LIB_PATH = OMP_LIB_PATH
+    return True
 
 
 def lib() -> C.CDLL:
@@ -85,6 +100,9 @@ def lib() -> C.CDLL:
         L.spral_ssids_cpu_create_num_subtree_dbl.argtypes = [
             C.c_bool, vp, vp, vp, vp, C.POINTER(CpuFactorOptions), C.POINTER(ThreadStats)]
         L.spral_ssids_cpu_destroy_num_subtree_dbl.argtypes = [C.c_bool, vp]
+        L.oracle_create_num_subtree_parallel.restype = vp
+        L.oracle_create_num_subtree_parallel.argtypes = [
+            C.c_bool, vp, vp, vp, C.POINTER(CpuFactorOptions), C.POINTER(ThreadStats)]
         for nm in ("fwd", "diag", "diag_bwd", "bwd"):
             f = getattr(L, f"spral_ssids_cpu_subtree_solve_{nm}_dbl")
             f.argtypes = [C.c_bool, vp, C.c_int, vp, C.c_int]
@@ -114,12 +132,14 @@ class OracleTree:
     """Whole assembly tree factorized as ONE SSIDS CPU subtree
     (spral/src/ssids/cpu/SymbolicSubtree.cxx:10-20, NumericSubtree.cxx:29-59)."""
 
-    def __init__(self, sym: dict, options: CpuFactorOptions | None = None):
+    def __init__(self, sym: dict, options: CpuFactorOptions | None = None, last_node: int | None = None):
+        """last_node: factorize only the nodes 1..last_node (a prefix of the postorder = a forest
+        of complete subtrees; bounded CPU samples of a large problem -- no solve then)."""
         self.L = lib()
         self.sym = sym
         self.opt = options or default_options()
         self.n = int(sym["n"])
-        nn = int(sym["nnodes"])
+        nn = int(sym["nnodes"]) if last_node is None else int(last_node)
         # keep the arrays alive: SSIDS borrows the pointers
         self._keep = [np.ascontiguousarray(sym[k]) for k in ("sptr", "sparent", "rptr", "rlist", "nptr", "nlist")]
         self._contrib_idx = np.zeros(1, dtype=np.int32)
@@ -136,8 +156,13 @@ class OracleTree:
         self._val = val
         self.posdef = posdef
         t0 = time.perf_counter()
-        self.num = self.L.spral_ssids_cpu_create_num_subtree_dbl(
-            posdef, self.symb, _p(val), _p(scaling), None, C.byref(self.opt), C.byref(self.stats))
+        if LIB_PATH == OMP_LIB_PATH:
+            # task-parallel build: the OpenMP parallel/single region SSIDS's Fortran caller provides
+            self.num = self.L.oracle_create_num_subtree_parallel(
+                posdef, self.symb, _p(val), _p(scaling), C.byref(self.opt), C.byref(self.stats))
+        else:
+            self.num = self.L.spral_ssids_cpu_create_num_subtree_dbl(
+                posdef, self.symb, _p(val), _p(scaling), None, C.byref(self.opt), C.byref(self.stats))
         return time.perf_counter() - t0
 
     def solve(self, b_perm: np.ndarray) -> np.ndarray:

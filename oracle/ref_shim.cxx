@@ -42,6 +42,24 @@ void spral_ssids_contrib_free_dbl(void *const) {
    abort();
 }
 
+// Task-parallel timing (liboracle_omp.so only; a plain call in the sequential build): SSIDS's
+// C++ creates OpenMP tasks but relies on its Fortran caller for the parallel region
+// (spral/src/ssids/fkeep.f90:226-230: "!$omp parallel proc_bind(close) default(shared)" +
+// "!$omp single" around the subtree factorization).  Same two directives here.
+void *spral_ssids_cpu_create_num_subtree_dbl(bool posdef, void const *symbolic_subtree, const double *aval,
+      const double *scaling, void **child_contrib, struct cpu_factor_options const *options, ThreadStats *stats);
+void *oracle_create_num_subtree_parallel(bool posdef, void const *symbolic_subtree, const double *aval,
+      const double *scaling, struct cpu_factor_options const *options, int *stats_out) {
+   void *res = nullptr;
+   #pragma omp parallel proc_bind(close) default(shared)
+   {
+      #pragma omp single
+      res = spral_ssids_cpu_create_num_subtree_dbl(posdef, symbolic_subtree, aval, scaling, nullptr, options,
+                                                   reinterpret_cast<ThreadStats *>(stats_out));
+   }
+   return res;
+}
+
 // align_lda as the reference was compiled (depends on -march): lets Python size buffers.
 long oracle_align_lda(long lda) { return (long) align_lda<double>((size_t) lda); }
 

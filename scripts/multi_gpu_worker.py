@@ -20,6 +20,9 @@ from sylver_b200 import gen
 
 
 def main():
+    import faulthandler
+    # a hang must leave evidence: every rank dumps its Python stack after SYLVER_WORKER_DUMP_S seconds
+    faulthandler.dump_traceback_later(int(os.environ.get("SYLVER_WORKER_DUMP_S", "240")), exit=True)
     kind, k = sys.argv[1], int(sys.argv[2])
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     posdef = not (len(sys.argv) > 4 and sys.argv[4] == "indef")      # "indef": APTP LDL^T on the same matrix
@@ -37,9 +40,11 @@ def main():
         n, ptr, row, val = (gen.laplacian_27pt if kind == "lap27" else gen.laplacian_7pt)(k)
         order = gen.nested_dissection_order(k)
     s = sb.Solver()
+    t_a = time.perf_counter()
     inf = s.analyse(n, ptr, row, order)
     assert inf.flag == 0
     flops = int(inf.num_flops)
+    print(f"[rank {rank}] analysed n={n} in {time.perf_counter() - t_a:.1f} s, flops {flops:.3e}", file=sys.stderr, flush=True)
     times = []
     for r in range(reps):
         dist.barrier(); torch.cuda.synchronize()
@@ -47,6 +52,7 @@ def main():
         inf = s.factorize(val, posdef=posdef)
         torch.cuda.synchronize(); dist.barrier()
         times.append(time.perf_counter() - t0)
+        print(f"[rank {rank}] factorization {r}: {times[-1]:.3f} s flag {inf.flag}", file=sys.stderr, flush=True)
         assert inf.flag == 0, inf.flag
     b = gen.sym_matvec(n, ptr, row, val, np.ones(n))
     x = s.solve(b)

@@ -94,6 +94,15 @@ def main():
             ms, nl, fl = prof[3 * i], prof[3 * i + 1], prof[3 * i + 2]
             print(f"  {KNAMES[i]:9s} {ms:10.3f} ms {100*ms/max(tot,1e-9):5.1f}%  launches {int(nl):6d}  "
                   f"alg GF {fl/1e9:12.2f}  -> {fl/max(ms,1e-9)/1e9:8.2f} TF/s")
+    if nk > 0:
+        lv = (C.c_double * 4096)()
+        nl = L.sylver_b200_numeric_tree_profile_levels(tree, lv, 4096)
+        et = s.engine_tree()
+        print("  per level (ms): " + " ".join(f"{k:>9s}" for k in KNAMES))
+        for l in range(nl):
+            row_ = [lv[l * 7 + c] for c in range(7)]
+            if sum(row_) > 0.05:
+                print(f"  level {l:3d}      " + " ".join(f"{v:9.3f}" for v in row_))
     fb, cb = C.c_long(0), C.c_long(0)
     L.sylver_b200_numeric_tree_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.sylver_b200_numeric_tree_bytes.restype = C.c_long

@@ -80,7 +80,7 @@ EXPORTS = [
     "sylver_b200_symbolic_tree_view",
     "sylver_b200_fkeep_tree", "sylver_b200_factor_front_posdef", "sylver_b200_factor_front_indef",
     "sylver_b200_bench_dmma", "sylver_b200_bench_copy", "sylver_b200_akeep_tree",
-    "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
+    "sylver_b200_numeric_tree_profile", "sylver_b200_numeric_tree_profile_levels", "sylver_b200_numeric_tree_bytes", "sylver_b200_set_stream",
     "sylver_b200_numeric_tree_get_front", "sylver_b200_numeric_tree_get_front_indef",
     "sylver_b200_comm_unique_id", "sylver_b200_comm_init", "sylver_b200_comm_finalize",
     "sylver_b200_comm_rank", "sylver_b200_comm_world", "sylver_b200_comm_set_virtual",
@@ -148,6 +148,7 @@ def lib() -> C.CDLL:
                                                  C.POINTER(C.c_float)]
     L.sylver_b200_numeric_tree_get_front_indef.argtypes = [vp, C.c_int, ip, vp, vp]
     L.sylver_b200_numeric_tree_profile.argtypes = [vp, dp, C.c_int]
+    L.sylver_b200_numeric_tree_profile_levels.argtypes = [vp, dp, C.c_int]
     L.sylver_b200_numeric_tree_bytes.restype = C.c_long
     L.sylver_b200_numeric_tree_bytes.argtypes = [vp, lp, lp]
     L.sylver_b200_set_stream.argtypes = [vp, C.c_int]

@@ -517,6 +517,11 @@ int sylver_b200_numeric_tree_profile(void const* tree, double* out, int cap) {
    return numeric_tree_profile(static_cast<const NumericTree*>(tree), out, cap);
 }
 
+int sylver_b200_numeric_tree_profile_levels(void const* tree, double* out, int cap) {
+   if (!tree) return -1;
+   return numeric_tree_profile_levels(static_cast<const NumericTree*>(tree), out, cap);
+}
+
 long sylver_b200_numeric_tree_bytes(void const* tree, long* factor_bytes, long* contrib_bytes) {
    if (!tree) return -1;
    return numeric_tree_bytes(static_cast<const NumericTree*>(tree), factor_bytes, contrib_bytes);

@@ -155,6 +155,42 @@ extern "C" double sylver_b200_bench_dmma(int kind, int n, int k, int iters) {
       cudaFree(dm); cudaFree(dn); cudaFree(dldl); cudaFree(dldc); cudaFree(dpar); cudaFree(dnch); cudaFree(dfr);
       cudaFree(dpre); cudaFree(dloff); cudaFree(dcoff); cudaFree(dcmo); cudaFree(L); cudaFree(C);
    }
+   else if (kind == 3 || kind == 4) {
+      // latency of the diagonal-block kernels on ONE 128 x 128 SPD block (microseconds per launch):
+      // kind 3 = k_potrf_inv_reg (column at a time), kind 4 = k_potrf_inv_blk (blocked)
+      const int m = 128, ld = 128;
+      std::vector<double> h((size_t)ld * m, 0.0);
+      for (int c = 0; c < m; ++c)
+         for (int r = c; r < m; ++r) h[(size_t)c * ld + r] = (r == c) ? 2.0 * m : 1.0 / (1.0 + r - c);
+      std::vector<int> hm{m}, hn{m}, hl{ld};
+      std::vector<long> ho{0};
+      int *dm, *dn, *dl, *dfr, *dfail;
+      long* dlo;
+      double *L, *L0, *Wd;
+      cudaMalloc(&dm, 4); cudaMalloc(&dn, 4); cudaMalloc(&dl, 4); cudaMalloc(&dfr, 4); cudaMalloc(&dfail, 16);
+      cudaMalloc(&dlo, 8); cudaMalloc(&L, h.size() * 8); cudaMalloc(&L0, h.size() * 8); cudaMalloc(&Wd, (size_t)m * m * 8);
+      cudaMemcpy(dm, hm.data(), 4, cudaMemcpyHostToDevice); cudaMemcpy(dn, hn.data(), 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(dl, hl.data(), 4, cudaMemcpyHostToDevice); cudaMemcpy(dlo, ho.data(), 8, cudaMemcpyHostToDevice);
+      cudaMemset(dfr, 0, 4); cudaMemset(dfail, 0, 16);
+      cudaMemcpy(L0, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+      DevTree T{};
+      T.m = dm; T.n = dn; T.ldl = dl; T.loff = dlo; T.L = L;
+      cudaFuncSetAttribute(k_potrf_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+      float best = 1e30f;
+      for (int i = 0; i < iters + 1; ++i) {
+         cudaMemcpy(L, L0, h.size() * 8, cudaMemcpyDeviceToDevice);
+         cudaDeviceSynchronize();
+         cudaEventRecord(e0);
+         if (kind == 3) k_potrf_inv_reg<<<1, PR_THREADS>>>(T, dfr, 0, 128, Wd, 128, dfail);
+         else k_potrf_inv_blk<<<1, PB_THREADS, PB_SMEM_BYTES>>>(T, dfr, 0, 128, Wd, 128, dfail);
+         cudaEventRecord(e1);
+         cudaEventSynchronize(e1);
+         float ms; cudaEventElapsedTime(&ms, e0, e1);
+         if (i > 0) best = std::min(best, ms);
+      }
+      result = best * 1e3;
+      cudaFree(dm); cudaFree(dn); cudaFree(dl); cudaFree(dfr); cudaFree(dfail); cudaFree(dlo); cudaFree(L); cudaFree(L0); cudaFree(Wd);
+   }
    cudaEventDestroy(e0); cudaEventDestroy(e1);
    if (cudaGetLastError() != cudaSuccess) return -1.0;
    return result;

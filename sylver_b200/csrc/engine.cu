@@ -752,6 +752,24 @@ static void build_posdef_plan(NumericTree* nt, bool device = true) {
       const double k = m - n;
       nt->prof_flops[KC_CONTRIB] += share * n * k * (k + 1);
    }
+   // algorithmic BYTES of the bandwidth-bound classes, reported through the same
+   // profile slots: extend-add = 8 B source + 16 B destination read-modify-write + 4 B index per
+   // contributed entry (the entries the two fused children deliver through the DMMA epilogue are
+   // not this kernel's); A scatter = 8 B value + 16 B (src, dest) pair + 8 B store per entry
+   nt->prof_flops[KC_SCATTER] = 32.0 * (double)st->nent;
+   for (int c = 0; c < N; ++c) {
+      const int p = st->parent[c];
+      if (p >= N || !in_dest(nt, p, me)) continue;
+      const double k = nt->m[c] - nt->n[c];
+      if (k <= 0) continue;
+      const int* cm = &st->cmap[st->cmapoff[c]];
+      double k0 = 0;
+      while (k0 < k && cm[(int)k0] < nt->n[p]) ++k0;
+      const bool fused = st->fchild[2 * (size_t)p] == c || st->fchild[2 * (size_t)p + 1] == c;
+      double entries = k0 * k - k0 * (k0 - 1) / 2.0;
+      if (!fused) entries += (k - k0) * (k - k0 + 1) / 2.0;
+      nt->prof_flops[KC_ASSEMBLE] += 28.0 * entries / nt->splitP[p];
+   }
    nt->W_doubles = wmax;
    if (!device) return;
    nt->d_prefix = dev_upload(prefix);
@@ -837,7 +855,10 @@ static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launch
       if (me == own) {
          {
             ProfScope ps(nt, KC_POTRF, s2);
-            k_potrf_inv_reg<<<1, PR_THREADS, 0, s2>>>(T, d_fr, si, nb, nt->d_Wsplit, wld, nt->d_fail);
+            if (nt->potrf_reg)
+               k_potrf_inv_reg<<<1, PR_THREADS, 0, s2>>>(T, d_fr, si, nb, nt->d_Wsplit, wld, nt->d_fail);
+            else
+               k_potrf_inv_blk<<<1, PB_THREADS, PB_SMEM_BYTES, s2>>>(T, d_fr, si, nb, nt->d_Wsplit, wld, nt->d_fail);
             ++launches;
          }
          if (m > p0 + pw) {
@@ -927,6 +948,7 @@ static void issue_posdef(NumericTree* nt) {
    }
    for (size_t l = 0; l < nt->levels.size(); ++l) {
       const LevelPlan& lp = nt->levels[l];
+      nt->prof_level = (int)l;
       const int* d_fr = nt->d_fac_nodes + lp.first;
       if (lp.count == 0) {
          for (const SplitPlan& sp : nt->splits[l]) issue_split_front(nt, sp, launches);
@@ -951,8 +973,10 @@ static void issue_posdef(NumericTree* nt) {
             k_potrf_inv<64><<<ls.cnt, 256, PotrfCfg<64>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
          else if (nt->potrf_old)
             k_potrf_inv<128><<<ls.cnt, 512, PotrfCfg<128>::SMEM, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
-         else
+         else if (nt->potrf_reg)
             k_potrf_inv_reg<<<ls.cnt, PR_THREADS, 0, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
+         else
+            k_potrf_inv_blk<<<ls.cnt, PB_THREADS, PB_SMEM_BYTES, q>>>(T, d_fr, (int)si, nb, nt->d_W, ls.wld, nt->d_fail);
          ++launches;
       };
       auto trsm = [&](size_t si, cudaStream_t q) {
@@ -1069,6 +1093,7 @@ static void set_kernel_attributes() {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm_batched, GT_THREADS, GT_SMEM_BYTES);
       fprintf(stderr, "sylver_b200: k_gemm_batched resident CTAs per SM: %d\n", nb);
    }
+   CU_TRY(cudaFuncSetAttribute(k_potrf_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<128>::SMEM));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<64>::SMEM));
    CU_TRY(cudaFuncSetAttribute(k_potrf_inv<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PotrfCfg<32>::SMEM));
@@ -1114,11 +1139,13 @@ static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
    nt->t_device = ms * 1e-3;
    if (nt->profile) {
       for (int c = 0; c < KC_COUNT; ++c) { nt->prof_ms[c] = 0; nt->prof_launches[c] = 0; }
+      nt->prof_level_ms.assign((size_t)nt->st->nlevels * KC_COUNT, 0.0);
       for (auto& e : nt->prof_events) {
          float t = 0;
          cudaEventElapsedTime(&t, e.second.first, e.second.second);
-         nt->prof_ms[e.first] += t;
-         nt->prof_launches[e.first]++;
+         nt->prof_ms[e.first & 255] += t;
+         nt->prof_launches[e.first & 255]++;
+         nt->prof_level_ms[(size_t)(e.first >> 8) * KC_COUNT + (e.first & 255)] += t;
       }
    }
    *stats = sylver_inform_c{};
@@ -1158,6 +1185,8 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       {
          const char* po = getenv("SYLVER_B200_POTRF_OLD");
          nt->potrf_old = po && po[0] == '1';
+         const char* pr = getenv("SYLVER_B200_POTRF_REG");
+         nt->potrf_reg = pr && pr[0] == '1';
          const char* pe = getenv("SYLVER_B200_PAIR");
          nt->pair_updates = !(pe && pe[0] == '0');
       }
@@ -1365,6 +1394,14 @@ int numeric_tree_profile(const NumericTree* nt, double* out, int cap) {
       out[3 * c + 2] = nt->prof_flops[c];
    }
    return KC_COUNT;
+}
+
+// per-level breakdown of the last profiled run: out[level * KC_COUNT + class] = ms; returns levels
+int numeric_tree_profile_levels(const NumericTree* nt, double* out, int cap) {
+   if (!nt->profile) return 0;
+   const int n = (int)nt->prof_level_ms.size();
+   for (int i = 0; i < n && i < cap; ++i) out[i] = nt->prof_level_ms[i];
+   return n / KC_COUNT;
 }
 
 int numeric_tree_get_front_indef(const NumericTree* nt, int node, int* nelim, double* d, int* perm) {

@@ -108,6 +108,7 @@ int device_count();
 // `val` if it is host memory, else a host copy in tmp (nullptr if the copy fails)
 const double* values_on_host(const double* val, size_t count, std::vector<double>& tmp);
 int numeric_tree_profile(const NumericTree* nt, double* out, int cap);
+int numeric_tree_profile_levels(const NumericTree* nt, double* out, int cap);
 void set_user_stream(void* stream, bool enable);
 long numeric_tree_bytes(const NumericTree* nt, long* factor_bytes, long* contrib_bytes);
 

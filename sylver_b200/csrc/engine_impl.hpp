@@ -166,8 +166,11 @@ struct NumericTree {
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
    bool profile = false;
    bool pair_updates = true;             // SYLVER_B200_PAIR=0: one rank-nb trailing update per block column
+   bool potrf_reg = false;               // SYLVER_B200_POTRF_REG=1: register-resident column-at-a-time kernel (A/B runs)
    bool potrf_old = false;               // SYLVER_B200_POTRF_OLD=1: shared-memory k_potrf_inv<128> (A/B runs)
-   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;   // class + 256 * level
+   int prof_level = 0;                   // tree level being issued (tags prof_events)
+   std::vector<double> prof_level_ms;    // [level * KC_COUNT + class] of the last profiled run
    double prof_ms[KC_COUNT] = {0};
    long prof_launches[KC_COUNT] = {0};
    double prof_flops[KC_COUNT] = {0};
@@ -238,7 +241,7 @@ struct ProfScope {
    ~ProfScope() {
       if (!nt->profile) return;
       cudaEventRecord(b, st);
-      nt->prof_events.push_back({cls, {a, b}});
+      nt->prof_events.push_back({cls + 256 * nt->prof_level, {a, b}});
    }
 };
 }  // namespace

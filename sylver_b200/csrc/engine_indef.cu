@@ -263,6 +263,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    for (int l = 0; l < st->nlevels; ++l) {
       const int gfirst = st->level_ptr[l], gcnt = st->level_ptr[l + 1] - gfirst;
       if (gcnt == 0) continue;
+      nt->prof_level = l;
       // ---- geometry of the level (children are complete: their nelim is known on every rank).
       // Sizes are computed for all fronts of the level, memory only for the fronts of this rank.
       order.clear();
@@ -516,11 +517,13 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    nt->launches = launches;
    if (nt->profile) {
       for (int c = 0; c < KC_COUNT; ++c) { nt->prof_ms[c] = 0; nt->prof_launches[c] = 0; }
+      nt->prof_level_ms.assign((size_t)nt->st->nlevels * KC_COUNT, 0.0);
       for (auto& e : nt->prof_events) {
          float t = 0;
          cudaEventElapsedTime(&t, e.second.first, e.second.second);
-         nt->prof_ms[e.first] += t;
-         nt->prof_launches[e.first]++;
+         nt->prof_ms[e.first & 255] += t;
+         nt->prof_launches[e.first & 255]++;
+         nt->prof_level_ms[(size_t)(e.first >> 8) * KC_COUNT + (e.first & 255)] += t;
       }
    }
    *stats = sylver_inform_c{};

@@ -938,4 +938,245 @@ k_potrf_inv_reg(DevTree T, const int* __restrict__ fronts, int step, int nb, dou
    }
 }
 
+// ---------------------------------------------------------------------------
+// Blocked 128 x 128 Cholesky + inverse on one SM -- the block-column critical path of the large
+// fronts (and of the multi-GPU panel chain).  Same contract as k_potrf_inv<128>.
+//
+// The column-at-a-time kernels above pay one CTA barrier (and a dependent rsqrt) per column,
+// 128 of them in sequence.  Here the block is factorized in four 32-column steps:
+//   (1) one warp holds the 32 x 32 diagonal block in registers (lane = row) and factorizes it
+//       with shuffles -- no barrier inside the 32 columns;
+//   (2) the rows below it are solved against L_jj^T, one thread per row, by substitution, while
+//       another warp forms the 32 x 32 inverse V_jj (lane = column);
+//   (3) the trailing blocks are updated with DMMA block products straight from shared memory.
+// The off-diagonal blocks of the inverse follow block sub-diagonal by sub-diagonal,
+//   V_ij = -V_ii (sum_{k=j}^{i-1} L_ik V_kj),  again as DMMA block products.
+// Shared memory: S (128 x 132: L in the lower triangle, V^T in the strict upper triangle of the
+// off-diagonal blocks), the four dense diagonal inverses, three product scratch blocks.
+// ---------------------------------------------------------------------------
+constexpr int PB_THREADS = 256;
+constexpr int PB_LD = 132;       // == 4 (mod 16): DMMA fragment loads are conflict free
+constexpr int PB_VLD = 36;
+constexpr size_t PB_SMEM_BYTES = ((size_t)128 * PB_LD + 4 * 32 * PB_VLD + 3 * 32 * PB_VLD + 128) * sizeof(double);
+
+// acc[ia][jb][h] += sum_{c < 32} X[ia*8 + g][c] * Y[jb*8 + 2*tq + h][c],  ia < NRA, jb < 4,
+// X[a][c] = xs[a*xrs + c*xks],  Y[b][c] = ys[b*yrs + c*yks]     (lane = 4*g + tq)
+template <int NRA>
+__device__ __forceinline__ void warp_blockprod32(double (&acc)[NRA][4][2], const double* xs, int xrs, int xks,
+                                                 const double* ys, int yrs, int yks) {
+   const int lane = threadIdx.x & 31;
+   const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+   for (int k4 = 0; k4 < 8; ++k4) {
+      double a[NRA], b[4];
+#pragma unroll
+      for (int ia = 0; ia < NRA; ++ia) a[ia] = xs[(ia * 8 + g) * xrs + (k4 * 4 + tq) * xks];
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) b[jb] = ys[(jb * 8 + g) * yrs + (k4 * 4 + tq) * yks];
+#pragma unroll
+      for (int ia = 0; ia < NRA; ++ia)
+#pragma unroll
+         for (int jb = 0; jb < 4; ++jb) dmma884(acc[ia][jb][0], acc[ia][jb][1], a[ia], b[jb]);
+   }
+}
+
+static __global__ void __launch_bounds__(PB_THREADS, 1)
+k_potrf_inv_blk(DevTree T, const int* __restrict__ fronts, int step, int nb, double* __restrict__ W, int wld,
+                int* fail) {
+   extern __shared__ __align__(16) double sm[];
+   double* S = sm;                           // S[r*PB_LD + c]
+   double* Vd = S + 128 * PB_LD;             // Vd[j][a*PB_VLD + b] = V_jj[a][b] (dense, zeros above the diagonal)
+   double* Tb = Vd + 4 * 32 * PB_VLD;        // three 32 x 32 scratch blocks
+   double* rinv = Tb + 3 * 32 * PB_VLD;      // 1 / L(r,r)
+   const int f = fronts[blockIdx.x];
+   const int n = T.n[f], ldl = T.ldl[f];
+   const int p0 = step * nb;
+   const int pw = min(nb, n - p0);
+   double* A = T.L + T.loff[f] + (size_t)p0 * ldl + p0;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int g = lane >> 2, tq = lane & 3;
+   const int nblk = (pw + 31) >> 5;
+   // ---- load the lower triangle (coalesced down the columns); identity outside pw ----
+   for (int c = warp; c < 32 * nblk; c += PB_THREADS / 32)
+      for (int r = lane; r < 32 * nblk; r += 32) {
+         double v = (r == c) ? 1.0 : 0.0;
+         if (r < pw && c < pw && r >= c) v = A[(size_t)c * ldl + r];
+         S[r * PB_LD + c] = v;
+      }
+   __syncthreads();
+   for (int j = 0; j < nblk; ++j) {
+      const int j0 = 32 * j;
+      if (warp == 0) {
+         // ---- (1) 32 x 32 Cholesky in registers: lane = row ----
+         double x[32];
+#pragma unroll
+         for (int c = 0; c < 32; ++c) x[c] = S[(j0 + lane) * PB_LD + j0 + c];
+         double rv = 1.0;
+         bool bad = false;
+#pragma unroll
+         for (int k = 0; k < 32; ++k) {
+            const double d = __shfl_sync(0xffffffffu, x[k], k);
+            const bool ok = d > 0.0;
+            bad |= !ok;
+            const double ri = ok ? rsqrt(d) : 1.0;
+            const double lk = (lane > k) ? x[k] * ri : (lane == k ? (ok ? d * ri : 1.0) : 0.0);
+            x[k] = lk;
+            if (lane == k) rv = ri;
+#pragma unroll
+            for (int c = k + 1; c < 32; ++c) {
+               const double lc = __shfl_sync(0xffffffffu, lk, c);
+               x[c] -= lk * lc;
+            }
+         }
+         if (bad && lane == 0) {
+            atomicExch(&fail[0], 1);
+            atomicMin(&fail[1], f);
+         }
+#pragma unroll
+         for (int c = 0; c < 32; ++c)
+            if (c <= lane) S[(j0 + lane) * PB_LD + j0 + c] = x[c];
+         rinv[j0 + lane] = rv;
+      }
+      __syncthreads();
+      if (warp == 7) {
+         // ---- (2b) V_jj = L_jj^{-1}: lane = column, rows in sequence (forward substitution) ----
+         double v[32];
+         const double* Lj = S + j0 * PB_LD + j0;
+#pragma unroll
+         for (int r = 0; r < 32; ++r) {
+            double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < r; k += 2) {
+               s0 -= Lj[r * PB_LD + k] * v[k];
+               if (k + 1 < r) s1 -= Lj[r * PB_LD + k + 1] * v[k + 1];
+            }
+            v[r] = (s0 + s1) * rinv[j0 + r];
+         }
+#pragma unroll
+         for (int r = 0; r < 32; ++r) Vd[j * 32 * PB_VLD + r * PB_VLD + lane] = v[r];
+      } else if (tid < 32 * (nblk - 1 - j)) {
+         // ---- (2a) rows below the diagonal block: w L_jj^T = a, one thread per row ----
+         const int row = j0 + 32 + tid;
+         double* Sr = S + row * PB_LD + j0;
+         const double* Lj = S + j0 * PB_LD + j0;
+         double w[32];
+#pragma unroll
+         for (int c = 0; c < 32; ++c) w[c] = Sr[c];
+#pragma unroll
+         for (int c = 0; c < 32; ++c) {
+            double s0 = w[c], s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < c; k += 2) {
+               s0 -= w[k] * Lj[c * PB_LD + k];
+               if (k + 1 < c) s1 -= w[k + 1] * Lj[c * PB_LD + k + 1];
+            }
+            w[c] = (s0 + s1) * rinv[j0 + c];
+         }
+#pragma unroll
+         for (int c = 0; c < 32; ++c) Sr[c] = w[c];
+      }
+      __syncthreads();
+      // ---- (3) trailing update: S_ik -= L_ij L_kj^T for i >= k > j, one 32 x 32 block per warp ----
+      {
+         const int nrem = nblk - 1 - j;
+         int t = warp, bi = 0, bk = 0;
+         bool have = false;
+         for (int i = 0; i < nrem && !have; ++i)
+            for (int k = 0; k <= i; ++k) {
+               if (t == 0) { bi = i; bk = k; have = true; break; }
+               --t;
+            }
+         if (have) {
+            const int i0 = j0 + 32 * (bi + 1), k0 = j0 + 32 * (bk + 1);
+            double acc[4][4][2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+               for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            warp_blockprod32<4>(acc, S + i0 * PB_LD + j0, PB_LD, 1, S + k0 * PB_LD + j0, PB_LD, 1);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+               for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) S[(i0 + a * 8 + g) * PB_LD + k0 + b * 8 + 2 * tq + h] -= acc[a][b][h];
+         }
+      }
+      __syncthreads();
+   }
+   // ---- L back to the panel (the update phase scribbled on the upper triangles: lower only) ----
+   for (int c = warp; c < pw; c += PB_THREADS / 32)
+      for (int r = c + lane; r < pw; r += 32) A[(size_t)c * ldl + r] = S[r * PB_LD + c];
+   __syncthreads();
+   // ---- off-diagonal blocks of the inverse, block sub-diagonal d: V_ij, i - j = d ----
+   for (int d = 1; d < nblk; ++d) {
+      const int ntask = nblk - d;                 // 3, 2, 1
+      const int wpt = (d == 1) ? 2 : 4;           // warps per task (16 or 8 rows each)
+      const int task = warp / wpt, part = warp % wpt;
+      const int rows = 32 / wpt;                  // 16 or 8
+      const bool have = task < ntask;
+      const int bi = d + task, bj = task;
+      const int i0 = 32 * bi, jj0 = 32 * bj;
+      const int a0 = part * rows;
+      double acc[2][4][2];
+      if (have) {
+#pragma unroll
+         for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+         // T = sum_k L_ik V_kj   (X = L_ik rows a0.., Y[b][c] = V_kj[c][b])
+         for (int k = bj; k < bi; ++k) {
+            const double* xs = S + (i0 + a0) * PB_LD + 32 * k;
+            const double* ys;
+            int yrs, yks;
+            if (k == bj) { ys = Vd + bj * 32 * PB_VLD; yrs = 1; yks = PB_VLD; }
+            else { ys = S + jj0 * PB_LD + 32 * k; yrs = PB_LD; yks = 1; }      // V_kj^T lives at S[j-rows][k-cols]
+            if (rows == 16) warp_blockprod32<2>(acc, xs, PB_LD, 1, ys, yrs, yks);
+            else warp_blockprod32<1>(reinterpret_cast<double(&)[1][4][2]>(acc), xs, PB_LD, 1, ys, yrs, yks);
+         }
+         double* Tt = Tb + task * 32 * PB_VLD;
+#pragma unroll
+         for (int a = 0; a < 2; ++a)
+            if (a * 8 < rows)
+#pragma unroll
+               for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) Tt[(a0 + a * 8 + g) * PB_VLD + b * 8 + 2 * tq + h] = acc[a][b][h];
+      }
+      __syncthreads();
+      if (have) {
+         // V_ij = -V_ii T   (X = Vd[i] rows a0.., Y[b][c] = T[c][b])
+#pragma unroll
+         for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+         const double* xs = Vd + bi * 32 * PB_VLD + a0 * PB_VLD;
+         const double* ys = Tb + task * 32 * PB_VLD;
+         if (rows == 16) warp_blockprod32<2>(acc, xs, PB_VLD, 1, ys, 1, PB_VLD);
+         else warp_blockprod32<1>(reinterpret_cast<double(&)[1][4][2]>(acc), xs, PB_VLD, 1, ys, 1, PB_VLD);
+         // transposed into the upper triangle: S[j0 + b][i0 + a] = V_ij[a][b]
+#pragma unroll
+         for (int a = 0; a < 2; ++a)
+            if (a * 8 < rows)
+#pragma unroll
+               for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h)
+                     S[(jj0 + b * 8 + 2 * tq + h) * PB_LD + i0 + a0 + a * 8 + g] = -acc[a][b][h];
+      }
+      __syncthreads();
+   }
+   // ---- W = V (lower), zero elsewhere; coalesced down the columns ----
+   double* Wf = W + (size_t)blockIdx.x * wld * wld;
+   for (int c = warp; c < wld; c += PB_THREADS / 32)
+      for (int r = lane; r < wld; r += 32) {
+         double v = 0.0;
+         if (r < pw && c < pw && r >= c) {
+            if ((r >> 5) == (c >> 5)) v = Vd[(r >> 5) * 32 * PB_VLD + (r & 31) * PB_VLD + (c & 31)];
+            else v = S[c * PB_LD + r];
+         }
+         Wf[r + (size_t)c * wld] = v;
+      }
+}
+
 }  // namespace sylver_b200
