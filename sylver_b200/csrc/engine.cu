@@ -1174,7 +1174,12 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
          nt->stream = g_user_stream;
          nt->own_stream = false;
       } else {
-         CU_TRY(cudaStreamCreateWithFlags(&nt->stream, cudaStreamNonBlocking));
+         // own streams: the main stream sits between the latency-critical chain stream (stream2,
+         // highest priority) and the bulk stream of the APTP contribution passes (stream3, lowest),
+         // so that the CTAs of a short chain kernel are dispatched before the queued bulk tiles
+         int plo = 0, phi = 0;
+         CU_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+         CU_TRY(cudaStreamCreateWithPriority(&nt->stream, cudaStreamNonBlocking, (plo + phi) / 2));
       }
       {
          const char* pe = getenv("SYLVER_B200_PROFILE");
@@ -1193,7 +1198,10 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       {
          const char* la = getenv("SYLVER_B200_LOOKAHEAD");
          if (!(la && la[0] == '0')) {
-            CU_TRY(cudaStreamCreateWithFlags(&nt->stream2, cudaStreamNonBlocking));
+            int plo = 0, phi = 0;
+            CU_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+            CU_TRY(cudaStreamCreateWithPriority(&nt->stream2, cudaStreamNonBlocking, phi));
+            CU_TRY(cudaStreamCreateWithPriority(&nt->stream3, cudaStreamNonBlocking, plo));
             CU_TRY(cudaEventCreateWithFlags(&nt->ev_next, cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&nt->ev_panel, cudaEventDisableTiming));
          }
@@ -1278,6 +1286,7 @@ void numeric_tree_destroy(NumericTree* nt) {
    if (nt->ev1) cudaEventDestroy(nt->ev1);
    if (nt->stream && nt->own_stream) cudaStreamDestroy(nt->stream);
    if (nt->stream2) cudaStreamDestroy(nt->stream2);
+   if (nt->stream3) cudaStreamDestroy(nt->stream3);
    if (nt->ev_next) cudaEventDestroy(nt->ev_next);
    if (nt->ev_panel) cudaEventDestroy(nt->ev_panel);
    for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }

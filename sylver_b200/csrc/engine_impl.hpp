@@ -160,7 +160,8 @@ struct NumericTree {
    DevTree T{};
    cudaStream_t stream = nullptr;
    bool own_stream = true;
-   cudaStream_t stream2 = nullptr;       // look-ahead: next panel's potrf + solve run beside the update
+   cudaStream_t stream2 = nullptr;       // look-ahead: next panel's potrf + solve run beside the update (high priority)
+   cudaStream_t stream3 = nullptr;       // APTP: per-panel contribution passes beside the pivoting chain (low priority)
    cudaEvent_t ev_next = nullptr, ev_panel = nullptr;
    cudaGraphExec_t graph = nullptr;
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
@@ -220,6 +221,8 @@ struct NumericTree {
    void* d_lvl = nullptr;                // per-level upload buffer (geometry updates, orders, prefixes)
    void* h_lvl = nullptr;                // pinned mirror
    size_t lvl_cap = 0;
+   cudaEvent_t ev_bulk = nullptr;        // bulk part of a panel's trailing update on stream3 (APTP look-ahead)
+   cudaEvent_t ev_cpass[2] = {nullptr, nullptr};   // per-panel contribution passes on stream2 (APTP)
    cudaEvent_t ev_lvl = nullptr;         // completion of the last H2D copy out of h_lvl
    bool lvl_busy = false;
    int* d_lvl_out = nullptr;             // nelim of the level's fronts (read back per level)

@@ -106,6 +106,8 @@ void indef_setup(NumericTree* nt) {
    CU_TRY(cudaMalloc(&nt->d_nelim, N * sizeof(int)));
    CU_TRY(cudaMalloc(&nt->d_stats, 8 * sizeof(int)));
    CU_TRY(cudaEventCreateWithFlags(&nt->ev_lvl, cudaEventDisableTiming));
+   for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreateWithFlags(&nt->ev_cpass[i], cudaEventDisableTiming));
+   CU_TRY(cudaEventCreateWithFlags(&nt->ev_bulk, cudaEventDisableTiming));
    nt->d_ldc = dev_upload(nt->ldc);
    nt->d_coff = dev_upload(nt->coff);
    nt->d_ncol0 = dev_upload(st->ncol);
@@ -130,6 +132,9 @@ void indef_destroy(NumericTree* nt) {
    if (nt->h_lvl) cudaFreeHost(nt->h_lvl);
    if (nt->h_lvl_out) cudaFreeHost(nt->h_lvl_out);
    if (nt->ev_lvl) cudaEventDestroy(nt->ev_lvl);
+   for (int i = 0; i < 2; ++i) { if (nt->ev_cpass[i]) cudaEventDestroy(nt->ev_cpass[i]); nt->ev_cpass[i] = nullptr; }
+   if (nt->ev_bulk) cudaEventDestroy(nt->ev_bulk);
+   nt->ev_bulk = nullptr;
    nt->ev_lvl = nullptr; nt->lvl_busy = false;
    nt->d_ncol0 = nullptr; nt->d_woff = nt->d_doff = nt->d_permoff = nullptr;
    nt->d_state = nullptr; nt->d_nelim = nt->d_stats = nullptr; nt->d_diag = nullptr;
@@ -249,6 +254,9 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
       const char* oe = getenv("SYLVER_B200_OB");
       if (oe && atoi(oe) >= IB) OB = atoi(oe) / IB * IB;
    }
+   // SYLVER_B200_APTP_LEGACY=1: round-1 launch sequence (apply / finish / swap as separate launches,
+   // one contribution update after the last panel) for A/B runs
+   const bool legacy = getenv("SYLVER_B200_APTP_LEGACY") && getenv("SYLVER_B200_APTP_LEGACY")[0] == '1';
    long launches = 0;
    for (auto& c : nt->chunks) c.used = 0;
    if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
@@ -439,12 +447,25 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          // a panel every block column consumes IB of them (passed or failed), so the launch
          // sequence is known to the host although the outcome of the pivoting is not.
          const int nouter = app_block ? (maxn + OB - 1) / OB : 0;
+         // Every completed outer panel updates the contribution block with its own pivots right
+         // away (mode 6), on the second stream: that pass only reads rows >= n of the panel's L and
+         // W columns, which nothing touches afterwards, so it runs beside the pivoting chain of the
+         // next panel instead of as one big update after the last one.  The panel's pivot range
+         // is published per parity slot (k_outer_end); a slot is reused two panels later.
+         const char* s2e = getenv("SYLVER_B200_APTP_S2");
+         cudaStream_t s2 = (nt->stream3 && !legacy && !(s2e && s2e[0] == '0')) ? nt->stream3 : s;
+         bool cpass[2] = {false, false};
+         bool bulk = false;
          int cnt_o = cnt;
          for (int o = 0; o < nouter; ++o) {
             while (cnt_o > 0 && nt->n[order[cnt_o - 1]] <= o * OB) --cnt_o;
             if (cnt_o == 0) break;
-            k_outer_begin<<<(cnt_o + 127) / 128, 128, 0, s>>>(T, d_fr, cnt_o, OB);
-            ++launches;
+            const int slot = o & 1;
+            if (s2 != s && cpass[slot]) CU_TRY(cudaStreamWaitEvent(s, nt->ev_cpass[slot], 0));
+            if (legacy) {
+               k_outer_begin<<<(cnt_o + 127) / 128, 128, 0, s>>>(T, d_fr, cnt_o, OB);
+               ++launches;
+            }
             int cnt_s = cnt_o;
             for (int ib = 0; ib < OB / IB; ++ib) {
                while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= o * OB + ib * IB) --cnt_s;
@@ -453,11 +474,17 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                TileBatch ub{d_fr, d_inn, cnt_s};
                {
                   ProfScope ps(nt, KC_POTRF);
-                  k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small);
-                  k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
-                  k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
-                  k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
-                  launches += 4;
+                  // the first block column of a panel also opens it (cnt_s == cnt_o then)
+                  k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small, (ib == 0 && !legacy) ? OB : 0);
+                  if (legacy) {
+                     k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
+                     k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
+                     k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
+                     launches += 4;
+                  } else {
+                     k_block_column32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
+                     launches += 2;
+                  }
                }
                {
                   // rest of the panel, including the columns that just failed (CTAs of fronts
@@ -467,18 +494,46 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                   ++launches;
                }
             }
-            if (nt->n[order[0]] > (o + 1) * OB || o > 0) {
+            const bool upd = nt->n[order[0]] > (o + 1) * OB || o > 0;
+            const bool split = upd && s2 != s;      // look-ahead: critical tile columns here, the rest on s2
+            if (upd) {
                // columns behind the panel exist (more candidates, or failed columns of earlier panels)
+               if (split && bulk) CU_TRY(cudaStreamWaitEvent(s, nt->ev_bulk, 0));      // previous panel's bulk part
                TileBatch ub{d_fr, d_upd, cnt_o};
                ProfScope ps(nt, KC_UPDATE);
-               k_gemm_batched<<<gemm_grid(5, upd_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 5, 0, IB, nullptr, 0, 0, 1);
-               k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr);
-               launches += 2;
-            } else {
-               k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr);
+               k_gemm_batched<<<gemm_grid(5, upd_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 5, split ? 1 : 0, IB, nullptr, 0, 0, 1);
                ++launches;
             }
+            k_outer_end<<<cnt_o, SW_THREADS, 0, s>>>(T, d_fr, slot);
+            ++launches;
+            if (!legacy && (split || con_prefix[cnt_o] > 0)) {
+               if (s2 != s) {
+                  CU_TRY(cudaEventRecord(nt->ev_panel, s));
+                  CU_TRY(cudaStreamWaitEvent(s2, nt->ev_panel, 0));
+               }
+               if (split) {
+                  TileBatch ub{d_fr, d_upd, cnt_o};
+                  ProfScope ps(nt, KC_UPDATE, s2);
+                  k_gemm_batched<<<gemm_grid(7, upd_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, ub, 7, slot, IB, nullptr, 0, 0, 1);
+                  ++launches;
+                  CU_TRY(cudaEventRecord(nt->ev_bulk, s2));
+                  bulk = true;
+               }
+               if (con_prefix[cnt_o] > 0) {
+                  TileBatch cb{d_fr, d_con, cnt_o};
+                  ProfScope ps(nt, KC_CONTRIB, s2);
+                  k_gemm_batched<<<gemm_grid(6, con_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, cb, 6, slot, IB, nullptr, 0, 0, 1);
+                  ++launches;
+               }
+               if (s2 != s) {
+                  CU_TRY(cudaEventRecord(nt->ev_cpass[slot], s2));
+                  cpass[slot] = true;
+               }
+            }
          }
+         if (bulk) CU_TRY(cudaStreamWaitEvent(s, nt->ev_bulk, 0));
+         for (int slot = 0; slot < 2; ++slot)
+            if (s2 != s && cpass[slot]) CU_TRY(cudaStreamWaitEvent(s, nt->ev_cpass[slot], 0));
          // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
          {
             ProfScope ps(nt, KC_ZERO);
@@ -488,11 +543,11 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          if (con_prefix[cnt] > 0) {
             TileBatch cb{d_fr, d_con, cnt};
             ProfScope ps(nt, KC_CONTRIB);
-            k_gemm_batched<<<gemm_grid(4, con_prefix[cnt]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, 0, IB, nullptr, 0, 0, 1);
+            k_gemm_batched<<<gemm_grid(4, con_prefix[cnt]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, cb, 4, legacy ? 1 : 0, IB, nullptr, 0, 0, 1);
             ++launches;
          }
          assemble(1);
-         k_front_stats<<<(cnt + 127) / 128, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out, d_slot);
+         k_front_stats<<<(cnt + 3) / 4, 128, 0, s>>>(T, d_fr, cnt, nt->d_stats, nt->d_lvl_out, d_slot);
          ++launches;
       }
       // ---- every rank learns the eliminated counts of the whole level ----

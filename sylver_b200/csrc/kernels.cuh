@@ -26,14 +26,23 @@ struct FrontState {
    int wb;       // width of the current block
    int nelim1;   // eliminated by the first (APTP) pass
    int nelim;    // eliminated in total; n - nelim columns are delayed to the parent
-   // two-level blocking: the candidates are processed in outer panels of up to 128 columns;
+   // two-level blocking: the candidates are processed in outer panels of up to 256 columns;
    // inside a panel the 32-wide block columns update only the panel, the rest of the front
    // gets one rank-(p0 - obeg) update per panel
    int obeg;     // first column eliminated by the current outer panel
    int oend;     // end of the current outer panel (<= na)
    int pa;       // end of the panel's active candidates; [pa, oend) failed inside this panel
+   int arrive;   // CTAs of the block-column kernel that finished the apply phase / the finish phase
+   int done;
    int pad;
+   // pivots [cb[s], ce[s]) of a completed outer panel, for its contribution-block pass (which runs
+   // on the second stream while the next panel is being factorized; s = panel parity)
+   int cb[2], ce[2];
+   // look-ahead: the panel's end and whether its failed columns had to be swapped behind the
+   // active candidates (then its whole trailing update ran on the critical path)
+   int co[2], cf[2];
 };
+static_assert(sizeof(FrontState) == 88, "FrontState layout");
 
 // Device view of the assembly tree (structure-of-arrays, one entry per front).
 struct DevTree {
@@ -164,6 +173,7 @@ constexpr int GT_LDA = 132;            // padded smem row strides (mod 16 == 4: 
 constexpr int GT_LDB = 68;
 constexpr int GT_STAGES = 4;
 constexpr int GT_LOOKAHEAD = 2;        // k-blocks in flight ahead of the one being consumed
+constexpr int GT_LOOKAHEAD_TCOLS = 3;  // APTP look-ahead: tile columns of a panel update that stay on the critical path
 constexpr int GT_WARPS = 8;            // consumer warps: 4 (rows) x 2 (columns), 32 x 32 each
 #ifndef GT_PRODUCER_WARP
 #define GT_PRODUCER_WARP 1             // 1: a ninth warp stages the operands (96-register cap); 0: the eight warps share the issue
@@ -579,18 +589,40 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       // mode 4: all eliminated columns -> contribution block
       const FrontState st = T.state[f];
       const double* Wf = T.W + T.woff[f];
-      const int kbeg = (mode == 3) ? st.kbeg : (mode == 5 ? st.obeg : 0);
-      t.K = (mode == 3) ? st.klen : (mode == 5 ? st.p0 - st.obeg : st.nelim);
-      if (mode != 4 && t.K == 0) return;
-      const int first = (mode == 3) ? st.p0 : (mode == 5 ? st.oend : n);     // first column/row of the updated region
+      // mode 6: pivots [cb, ce) of the completed outer panel of parity `step` -> contribution block
+      // mode 4: pivots the second pass (TPP) eliminated, [nelim1, nelim) -> contribution block
+      //         (step = 1: all pivots [0, nelim), the round-1 sequence without per-panel passes)
+      // The pass that applies pivot 0 overwrites the block (and gathers the fused children); the
+      // later ones read-modify-write it.  A front that eliminates nothing is written by mode 4.
+      const bool contrib = mode == 4 || mode == 6;
+      // Look-ahead split of the panel -> rest update (mode 5 with step = 1 / mode 7): the first
+      // three tile columns hold the next panel's candidates and are updated on the critical path
+      // (mode 5, live state); the rest (mode 7, from the snapshot k_outer_end published in slot
+      // `step`) runs on the bulk stream beside the next panel's pivoting chain.  A panel whose
+      // failed columns must be swapped with candidates from the far end (ns > 0) keeps its whole
+      // update on the critical path: the swap reads rows and columns of the tail.
+      const int sl = step & 1;
+      const int kbeg = (mode == 3) ? st.kbeg : (mode == 5 ? st.obeg : (mode == 7 ? st.cb[sl] : (mode == 6 ? st.cb[sl] : (step ? 0 : st.nelim1))));
+      t.K = (mode == 3) ? st.klen : (mode == 5 ? st.p0 - st.obeg : ((mode == 6 || mode == 7) ? st.ce[sl] - kbeg : st.nelim - kbeg));
+      const bool first_pass = contrib && kbeg == 0;
+      if (t.K == 0 && !(mode == 4 && first_pass)) return;
+      const int first = (mode == 3) ? st.p0 : (mode == 5 ? st.oend : (mode == 7 ? st.co[sl] : n));     // first column/row of the updated region
       const int base = first & ~1;
-      const int cend = (mode == 3) ? st.oend : (mode == 5 ? n : m);
+      const int cend = (mode == 3) ? st.oend : ((mode == 5 || mode == 7) ? n : m);
       if (cend <= first) return;
+      int tj_lo = 0, tj_hi = 0x7fffffff;
+      if (mode == 5 && step == 1) {
+         const int ns = min(st.oend - st.p0, st.na - st.oend);
+         if (ns <= 0) tj_hi = GT_LOOKAHEAD_TCOLS;
+      } else if (mode == 7) {
+         if (st.cf[sl]) return;
+         tj_lo = GT_LOOKAHEAD_TCOLS;
+      }
       const int TR = (m - base + GT_BM - 1) / GT_BM;
       const int TC = (cend - base + GT_BN - 1) / GT_BN;
       int tj = 0;
       while (tj < TC && local >= TR - tj) { local -= TR - tj; ++tj; }
-      if (tj >= TC) return;
+      if (tj >= TC || tj < tj_lo || tj >= tj_hi) return;
       const int ti = tj + local;
       i0 = base + ti * GT_BM;
       j0 = base + tj * GT_BN + half * GT_HN;
@@ -599,12 +631,12 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       t.A = Wf + (size_t)kbeg * ldl + i0;
       t.B = Lf + (size_t)kbeg * ldl + j0;
       t.lda = t.ldb = ldl;
-      if (mode != 4) {
+      if (!contrib) {
          d.dbase = Lf; d.ldd = ldl; d.clo = first; d.chi = cend; d.rmin = 0; d.lower = true; d.op = 0;
       } else {
          const int ldc = T.ldc[f];
          d.dbase = T.C + T.coff[f] - (size_t)n * ldc - n; d.ldd = ldc; d.clo = n; d.chi = m; d.rmin = 0; d.lower = true;
-         d.op = 1;      // the other children are extend-added afterwards (k_assemble_indef part 1)
+         d.op = first_pass ? 1 : 0;      // the other children are extend-added afterwards (k_assemble_indef part 1)
       }
    } else {
       const int base = (mode == 0) ? (p0 + pw) : (n & ~1);

@@ -44,16 +44,27 @@ struct DiagScratch {
    int pad[2];
 };
 
+// begin_ob > 0: this is the first block column of an outer panel of up to begin_ob candidates
+// (what k_outer_begin did in a launch of its own).
 static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int* __restrict__ fronts,
-                                                           DiagScratch* __restrict__ scratch, double u, double small) {
+                                                           DiagScratch* __restrict__ scratch, double u, double small,
+                                                           int begin_ob) {
    __shared__ double S[IB * SLD];
    __shared__ double dinv[2 * IB + 2];
    __shared__ int lperm[IB];
    const int f = fronts[blockIdx.x];
    FrontState& st = T.state[f];
+   const int lane = threadIdx.x;
+   if (begin_ob > 0) {
+      if (lane == 0) {
+         st.obeg = st.p0;
+         st.oend = min(st.p0 + begin_ob, st.na);
+         st.pa = st.oend;
+      }
+      __syncwarp();
+   }
    const int p0 = st.p0;
    const int wb = min(IB, st.pa - p0);
-   const int lane = threadIdx.x;
    if (lane == 0) st.wb = wb;
    if (wb <= 0) return;
    const int ldl = T.ldl[f];
@@ -480,6 +491,193 @@ static __global__ void __launch_bounds__(SW_THREADS) k_swap_failed(DevTree T, co
    }
 }
 
+// ---------------------------------------------------------------------------
+// k_block_column32: k_apply32 + k_finish32 + k_swap_failed in ONE launch.
+//   phase A  every CTA of the front applies the pivots to its rows (w kept in registers) and
+//            lowers npass; the row permutation of the columns left of the block is done here too
+//   phase B  front-wide rendezvous: the CTAs of a front have consecutive block indices and are
+//            dispatched in order, so the ones that arrived can wait for the rest (a front has at
+//            most 1 + m/256 of them, far fewer than fit on the GPU at once)
+//   phase C  with the pass count final, every CTA writes its rows in place (k_finish32)
+//   phase D  the LAST CTA to finish moves the failed columns behind the active candidates and
+//            advances the front state (k_swap_failed)
+// One thread = one row; chunk 0 = the diagonal block.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(AP_THREADS) k_block_column32(DevTree T, TileBatch batch,
+                                                                      const DiagScratch* __restrict__ scratch, double u,
+                                                                      double small) {
+   __shared__ double Lb[IB * SLD];
+   __shared__ double Ao[IB * SLD];
+   __shared__ double dinv[2 * IB + 2];
+   __shared__ int lperm[IB];
+   __shared__ int operm[IB];
+   __shared__ int s_fail, s_npass, s_last;
+   const int item = blockIdx.x;
+   const int fi = find_front(batch, item);
+   const int f = batch.fronts[fi];
+   const int chunk = item - batch.prefix[fi];
+   FrontState& gst = T.state[f];
+   const FrontState st = gst;
+   const int wb = st.wb;
+   if (wb <= 0) return;
+   const int p0 = st.p0;
+   const int m = T.m[f], n = T.n[f], ldl = T.ldl[f];
+   // at least one row chunk even when no row lies below the block (root fronts): it still has
+   // to permute the rows of the columns left of the block
+   const int nrowchunks = max((m - (p0 + wb) + AP_THREADS - 1) / AP_THREADS, 1);
+   const int nexp = 1 + nrowchunks;                    // CTAs of this front that take part
+   if (chunk >= nexp) return;
+   const int nchunks = batch.prefix[fi + 1] - batch.prefix[fi];
+   const DiagScratch& ds = scratch[fi];
+   for (int i = threadIdx.x; i < IB * SLD; i += AP_THREADS) Lb[i] = ds.S[i];
+   if (threadIdx.x < 2 * IB + 2) dinv[threadIdx.x] = ds.dinv[threadIdx.x];
+   if (threadIdx.x < IB) lperm[threadIdx.x] = ds.lperm[threadIdx.x];
+   if (threadIdx.x == 0) s_fail = IB;
+   __syncthreads();
+   double* Lf = T.L + T.loff[f];
+   double* Wf = T.W + T.woff[f];
+   const int r = p0 + wb + (chunk - 1) * AP_THREADS + threadIdx.x;
+   const bool rowthread = chunk >= 1 && r < m;
+   double w[IB];
+   // ---------------- phase A ----------------
+   if (chunk == 0) {
+      const double* A = Lf + (size_t)p0 * ldl + p0;
+      for (int i = threadIdx.x; i < IB * IB; i += AP_THREADS) {
+         const int rr = i & (IB - 1), cc = i >> 5;
+         double v = 0.0;
+         if (rr < wb && cc < wb) v = (rr >= cc) ? A[(size_t)cc * ldl + rr] : A[(size_t)rr * ldl + cc];
+         Ao[rr * SLD + cc] = v;
+      }
+      if (threadIdx.x < wb) operm[threadIdx.x] = T.perm[T.permoff[f] + p0 + threadIdx.x];
+   } else {
+      // rows p0..p0+wb of the L columns left of the block (apply_rperm): one warp per column, one
+      // lane per row, shared between the row chunks; skipped when the block did not permute.  The W
+      // panel is NOT permuted (its candidate rows are dead after the block column's own update).
+      const int lane = threadIdx.x & 31;
+      const int src = (lane < wb) ? lperm[lane] : lane;
+      if (__any_sync(0xffffffffu, src != lane)) {
+         const int nw = AP_THREADS / 32;
+         for (int c = (chunk - 1) * nw + (threadIdx.x >> 5); c < p0; c += nrowchunks * nw) {
+            double* col = Lf + (size_t)c * ldl + p0;
+            const double v = (lane < wb) ? col[src] : 0.0;
+            __syncwarp();
+            if (lane < wb) col[lane] = v;
+         }
+      }
+      int fail = IB;
+      if (rowthread) {
+         const double* Ar = Lf + (size_t)p0 * ldl + r;
+         double* Wr = Wf + (size_t)p0 * ldl + r;
+#pragma unroll
+         for (int j = 0; j < IB; ++j) w[j] = (j < wb) ? Ar[(size_t)lperm[j] * ldl] : 0.0;
+#pragma unroll
+         for (int j = 1; j < IB; ++j) {
+            double s = w[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= w[k] * Lb[j * SLD + k];
+            w[j] = s;
+         }
+         const double lim = 1.0 / u;
+#pragma unroll
+         for (int j = 0; j < IB; ++j) {
+            if (j < wb) {
+               double cs, co;
+               int kind;
+               pivot_coefs(dinv, wb, j, cs, co, kind);
+               const double wo = (kind == 1) ? w[(j + 1) & (IB - 1)] : w[(j + IB - 1) & (IB - 1)];
+               double l;
+               if (kind == 3) l = (fabs(w[j]) < small) ? 0.0 : INFINITY * w[j];
+               else l = cs * w[j] + ((kind == 0) ? 0.0 : co * wo);
+               if (!(fabs(l) <= lim) && fail == IB) fail = j;      // NaN fails too
+               Wr[(size_t)j * ldl] = w[j];
+            }
+         }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fail = min(fail, __shfl_xor_sync(0xffffffffu, fail, o));
+      if ((threadIdx.x & 31) == 0 && fail < IB) atomicMin(&s_fail, fail);
+   }
+   __syncthreads();
+   // ---------------- phase B: rendezvous ----------------
+   if (threadIdx.x == 0) {
+      if (s_fail < IB) atomicMin(&gst.npass, s_fail);
+      __threadfence();
+      atomicAdd(&gst.arrive, 1);
+      while (atomicAdd(&gst.arrive, 0) < nexp) __nanosleep(64);
+      __threadfence();
+      s_npass = atomicAdd(&gst.npass, 0);
+   }
+   __syncthreads();
+   // ---------------- phase C: finish ----------------
+   const int npass = adjusted_pass(min(s_npass, wb), dinv);
+   if (chunk == 0) {
+      for (int i = threadIdx.x; i < IB * IB; i += AP_THREADS) {
+         const int rr = i & (IB - 1), cc = i >> 5;
+         if (rr < wb && cc < wb && rr >= cc) {
+            double v;
+            if (cc < npass) v = (rr == cc) ? 1.0 : Lb[rr * SLD + cc];
+            else v = Ao[lperm[rr] * SLD + lperm[cc]];
+            Lf[(size_t)(p0 + cc) * ldl + p0 + rr] = v;
+            if (cc < npass && rr > cc) Wf[(size_t)(p0 + cc) * ldl + p0 + rr] = Lb[cc * SLD + rr];
+         }
+      }
+      int* perm = T.perm + T.permoff[f] + p0;
+      if (threadIdx.x < wb) perm[threadIdx.x] = operm[lperm[threadIdx.x]];
+      double* D = T.D + T.doff[f] + 2 * (size_t)p0;
+      if (threadIdx.x < 2 * npass) D[threadIdx.x] = dinv[threadIdx.x];
+   } else if (rowthread) {
+      double* Ar = Lf + (size_t)p0 * ldl + r;
+      double out[IB];
+#pragma unroll
+      for (int j = 0; j < IB; ++j) {
+         if (j < npass) {
+            double cs, co;
+            int kind;
+            pivot_coefs(dinv, wb, j, cs, co, kind);
+            const double wo = (kind == 1) ? w[(j + 1) & (IB - 1)] : w[(j + IB - 1) & (IB - 1)];
+            if (kind == 3) out[j] = (fabs(w[j]) < small) ? 0.0 : INFINITY * w[j];
+            else if (kind == 0) out[j] = cs * w[j];
+            else out[j] = cs * w[j] + co * wo;
+         } else if (j < wb) {
+            out[j] = Ar[(size_t)lperm[j] * ldl];      // failed: the original entry, column-permuted
+         }
+      }
+#pragma unroll
+      for (int j = 0; j < IB; ++j)
+         if (j < wb) Ar[(size_t)j * ldl] = out[j];
+   }
+   // ---------------- phase D: the last CTA advances the front ----------------
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&gst.done, 1) == nexp - 1) ? 1 : 0;
+   }
+   __syncthreads();
+   if (!s_last) return;
+   __threadfence();
+   {
+      const int pa = st.pa;
+      const int nf = wb - npass;
+      const int q = pa - p0 - wb;
+      const int ns = min(nf, q);
+      if (ns > 0) {
+         int* perm = T.perm + T.permoff[f];
+         for (int i = 0; i < ns; ++i) cta_sym_swap(Lf, Wf, perm, ldl, m, n, p0 + npass, p0 + npass + i, pa - ns + i, p0);
+      }
+      if (threadIdx.x == 0) {
+         gst.kbeg = p0;
+         gst.klen = npass;
+         gst.p0 = p0 + npass;
+         gst.pa = pa - nf;       // failed columns stay inside the outer panel (they keep receiving its updates)
+         gst.npass = IB;
+         gst.wb = 0;
+         gst.arrive = 0;
+         gst.done = 0;
+      }
+   }
+   (void)nchunks;
+}
+
 // Outer panel of the two-level blocking: up to OB candidates.
 constexpr int OB_DEFAULT = 256;      // SYLVER_B200_OB overrides (multiple of 32)
 static __global__ void k_outer_begin(DevTree T, const int* __restrict__ fronts, int cnt, int OB) {
@@ -493,11 +691,19 @@ static __global__ void k_outer_begin(DevTree T, const int* __restrict__ fronts, 
 // After the panel's rank-(p0 - obeg) update of the columns behind it, every column >= p0 has
 // seen the same pivots: the panel's failed columns [p0, oend) move behind the still-active
 // candidates (one CTA per front).
-static __global__ void __launch_bounds__(SW_THREADS) k_outer_end(DevTree T, const int* __restrict__ fronts) {
+// `slot` (panel parity): the panel's pivots [obeg, p0) are published in cb/ce[slot] for its
+// contribution-block pass (k_gemm_batched mode 6).
+static __global__ void __launch_bounds__(SW_THREADS) k_outer_end(DevTree T, const int* __restrict__ fronts, int slot) {
    const int f = fronts[blockIdx.x];
    FrontState& st = T.state[f];
    const int p0 = st.p0, na = st.na, oend = st.oend;
    const int nf = oend - p0;
+   if (threadIdx.x == 0) {
+      st.cb[slot] = st.obeg;
+      st.ce[slot] = p0;
+      st.co[slot] = oend;
+      st.cf[slot] = min(nf, na - oend) > 0 ? 1 : 0;
+   }
    if (nf <= 0) return;
    const int ns = min(nf, na - oend);
    __syncthreads();
@@ -713,9 +919,13 @@ static __global__ void __launch_bounds__(TPP_THREADS) k_tpp(DevTree T, const int
 // factor_failed.hxx:64,118-127).  One thread per front.
 // stats: [0] num_delay [1] num_neg [2] num_two [3] num_zero [4] not_first_pass [5] not_second_pass
 // ---------------------------------------------------------------------------
-static __global__ void k_front_stats(DevTree T, const int* __restrict__ fronts, int cnt, int* __restrict__ stats,
-                                     int* __restrict__ nelim_out, const int* __restrict__ slot) {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per front, lanes stride the columns: a column is the second of a 2x2 pivot iff its
+// first D entry is Inf (the reference's storage convention), so every column classifies itself.
+static __global__ void __launch_bounds__(128) k_front_stats(DevTree T, const int* __restrict__ fronts, int cnt,
+                                                            int* __restrict__ stats, int* __restrict__ nelim_out,
+                                                            const int* __restrict__ slot) {
+   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
    if (i >= cnt) return;
    const int f = fronts[i];
    const FrontState st = T.state[f];
@@ -723,12 +933,12 @@ static __global__ void k_front_stats(DevTree T, const int* __restrict__ fronts, 
    const int nelim = st.nelim;
    const double* d = T.D + T.doff[f];
    int neg = 0, two = 0, zero = 0;
-   for (int j = 0; j < nelim;) {
+   for (int j = lane; j < nelim; j += 32) {
       const double a11 = d[2 * j], a21 = d[2 * j + 1];
+      if (!isfinite(a11)) continue;                          // second column of a 2x2
       if (j + 1 == nelim || isfinite(d[2 * j + 2])) {
          if (a11 == 0.0) ++zero;
          if (a11 < 0.0) ++neg;
-         ++j;
       } else {
          const double a22 = d[2 * j + 3];
          ++two;
@@ -736,9 +946,15 @@ static __global__ void k_front_stats(DevTree T, const int* __restrict__ fronts, 
          const double trace = a11 + a22;
          if (det < 0) ++neg;
          else if (trace < 0) neg += 2;
-         j += 2;
       }
    }
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      neg += __shfl_xor_sync(0xffffffffu, neg, o);
+      two += __shfl_xor_sync(0xffffffffu, two, o);
+      zero += __shfl_xor_sync(0xffffffffu, zero, o);
+   }
+   if (lane != 0) return;
    nelim_out[slot[i]] = nelim;      // the front's position in the level's global list
    if (n - nelim) atomicAdd(&stats[0], n - nelim);
    if (neg) atomicAdd(&stats[1], neg);
@@ -762,7 +978,8 @@ static __global__ void __launch_bounds__(256) k_init_front(DevTree T, const int*
    if (threadIdx.x == 0) {
       FrontState s;
       s.p0 = 0; s.na = T.n[f]; s.npass = IB; s.kbeg = 0; s.klen = 0; s.wb = 0; s.nelim1 = 0; s.nelim = 0;
-      s.obeg = 0; s.oend = 0; s.pa = 0; s.pad = 0;
+      s.obeg = 0; s.oend = 0; s.pa = 0; s.arrive = 0; s.done = 0; s.pad = 0;
+      s.cb[0] = s.cb[1] = 0; s.ce[0] = s.ce[1] = 0; s.co[0] = s.co[1] = 0; s.cf[0] = s.cf[1] = 0;
       T.state[f] = s;
    }
 }
