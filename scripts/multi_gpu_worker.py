@@ -73,6 +73,7 @@ def main():
                               fwd_bwd_vs_full=agree, launches=tm["launches"])), flush=True)
     assert be <= 1e-14, be
     assert agree <= 1e-12
+    s.free()                 # numeric trees (and any graph holding NCCL nodes) go before the communicator
     sb.lib().sylver_b200_comm_finalize()
     dist.barrier()
     dist.destroy_process_group()

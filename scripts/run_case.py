@@ -43,7 +43,7 @@ def dense(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("kind", choices=["lap7", "lap27", "kkt", "dense"])
+    ap.add_argument("kind", choices=["lap7", "lap27", "kkt", "kktd", "dense"])
     ap.add_argument("k", type=int)
     ap.add_argument("--ncol", type=int, default=0, help="dense: fully-summed columns (default m/4)")
     ap.add_argument("--delays", action="store_true", help="dense: apply cause_delays")
@@ -62,8 +62,9 @@ def main():
         n, ptr, row, val = gen.laplacian_27pt(a.k)
         order = gen.nested_dissection_order(a.k)
     else:
-        n, ptr, row, val = gen.stokes_kkt(a.k)
+        n, ptr, row, val = (gen.stokes_kkt if a.kind == "kkt" else gen.stokes_kkt_delays)(a.k)
         order = gen.nested_dissection_order(a.k, dofs_per_cell=4)
+        a.indef = True
     t1 = time.time()
     s = sb.Solver()
     inf = s.analyse(n, ptr, row, order)

@@ -867,15 +867,13 @@ static void issue_split_front(NumericTree* nt, const SplitPlan& sp, long& launch
             k_gemm_batched<<<gemm_grid(2, tiles), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, b, 2, si, nb, nt->d_Wsplit, wld, 0, 1);
             ++launches;
          }
-         CU_TRY(cudaMemcpy2DAsync(nt->d_stage, (size_t)rows * sizeof(double), Lf + (size_t)p0 * ldl + p0,
-                                  (size_t)ldl * sizeof(double), (size_t)rows * sizeof(double), pw,
-                                  cudaMemcpyDeviceToDevice, s2));
       }
-      if (comm_bcast(nt->d_stage, (size_t)rows * pw, own, sp.gid, s2)) throw CudaFailure{-52};
-      if (me != own)
-         CU_TRY(cudaMemcpy2DAsync(Lf + (size_t)p0 * ldl + p0, (size_t)ldl * sizeof(double), nt->d_stage,
-                                  (size_t)rows * sizeof(double), (size_t)rows * sizeof(double), pw,
-                                  cudaMemcpyDeviceToDevice, s2));
+      // The panel travels IN PLACE: every member keeps the front at the same leading dimension, so
+      // the span from L(p0, p0) to L(m-1, p0+pw-1) is one contiguous piece of the arena on both
+      // sides (it includes the rows above p0 of the later columns -- the zero upper triangle);
+      // no pack / unpack copies around the broadcast.
+      const size_t span = (size_t)(pw - 1) * ldl + (size_t)rows;
+      if (comm_bcast(Lf + (size_t)p0 * ldl + p0, span, own, sp.gid, s2)) throw CudaFailure{-52};
    };
    // trailing update by block column si: tile columns tstart, tstart + tstep, ... of the grid that
    // starts at column (si + 1) * nb (tile column tj = block column si + 1 + tj)
@@ -1123,7 +1121,7 @@ void load_values(NumericTree* nt, const double* aval, const double* scaling) {
 
 static void run_posdef(NumericTree* nt, sylver_inform_c* stats) {
    CU_TRY(cudaEventRecord(nt->ev0, nt->stream));
-   if (nt->profile || nt->world > 1) {
+   if (nt->profile || !nt->graph) {
       for (auto& e : nt->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
       nt->prof_events.clear();
       issue_posdef(nt);      // NCCL exchanges are issued eagerly, level by level
@@ -1227,14 +1225,37 @@ NumericTree* numeric_tree_create(bool posdef, SymbolicTree* st, const double* av
       CU_TRY(cudaMalloc(&nt->d_C, nt->C_doubles * sizeof(double)));
       CU_TRY(cudaMalloc(&nt->d_W, nt->W_doubles * sizeof(double)));
       upload_geometry(nt);
-      // capture the launch sequence once
-      if (!nt->profile && nt->world == 1) {
+      // capture the launch sequence once.  Multi-GPU runs over NCCL can capture it as well (the
+      // exchanges and panel broadcasts become graph nodes; every rank replays the same sequence).
+      // The in-process fabric (rank threads, host-side rendezvous) cannot be captured.
+      // Opt-in (SYLVER_B200_GRAPH_MULTI=1): measured on 2 x B200 the replayed graph is no faster than
+      // the eager issue (149.83 vs 149.87 ms on lap27_100, profiles/r2_two_gpu.md), and a graph that
+      // holds NCCL nodes must be destroyed before its communicator.
+      {
+         const char* gm = getenv("SYLVER_B200_GRAPH_MULTI");
+         nt->graph_multi = nt->world > 1 && comm().nccl != nullptr && gm && gm[0] == '1';
+      }
+      if (!nt->profile && (nt->world == 1 || nt->graph_multi)) {
          cudaGraph_t g = nullptr;
          CU_TRY(cudaStreamBeginCapture(nt->stream, cudaStreamCaptureModeThreadLocal));
-         issue_posdef(nt);
-         CU_TRY(cudaStreamEndCapture(nt->stream, &g));
-         CU_TRY(cudaGraphInstantiate(&nt->graph, g, 0));
-         CU_TRY(cudaGraphDestroy(g));
+         bool captured = true;
+         try {
+            issue_posdef(nt);
+         } catch (CudaFailure&) {
+            if (!nt->graph_multi) throw;
+            captured = false;      // a collective that cannot be captured: eager issue instead
+         }
+         cudaError_t ce = cudaStreamEndCapture(nt->stream, &g);
+         if (captured && ce == cudaSuccess && g) {
+            CU_TRY(cudaGraphInstantiate(&nt->graph, g, 0));
+         } else if (!nt->graph_multi) {
+            CU_TRY(ce);
+         } else {
+            cudaGetLastError();
+            fprintf(stderr, "sylver_b200: multi-GPU launch sequence not capturable (%s), issuing eagerly\n",
+                    cudaGetErrorName(ce));
+         }
+         if (g) CU_TRY(cudaGraphDestroy(g));
       }
       load_values(nt, aval, scaling);
       run_posdef(nt, stats);

@@ -164,6 +164,7 @@ struct NumericTree {
    cudaStream_t stream3 = nullptr;       // APTP: per-panel contribution passes beside the pivoting chain (low priority)
    cudaEvent_t ev_next = nullptr, ev_panel = nullptr;
    cudaGraphExec_t graph = nullptr;
+   bool graph_multi = false;             // world > 1: the NCCL launch sequence is captured too
    // profiling (SYLVER_B200_PROFILE=1): per-class device time / launches / algorithmic flops
    bool profile = false;
    bool pair_updates = true;             // SYLVER_B200_PAIR=0: one rank-nb trailing update per block column

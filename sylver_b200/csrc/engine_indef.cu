@@ -71,7 +71,7 @@ static void ensure_cap(T*& dptr, size_t& cap, size_t need) {
 void indef_setup(NumericTree* nt) {
    // kernels.cuh kernels are per translation unit (static __global__): this TU's copy needs its
    // own opt-in to > 48 KB of dynamic shared memory
-   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
@@ -454,6 +454,10 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          // is published per parity slot (k_outer_end); a slot is reused two panels later.
          const char* s2e = getenv("SYLVER_B200_APTP_S2");
          cudaStream_t s2 = (nt->stream3 && !legacy && !(s2e && s2e[0] == '0')) ? nt->stream3 : s;
+         // SYLVER_B200_APTP_BULK1=1: bulk launches beside the pivoting chain ask for enough shared
+         // memory that only ONE of their CTAs fits per SM, leaving room for the chain's kernels
+         const char* b1e = getenv("SYLVER_B200_APTP_BULK1");
+         const size_t bulk_smem = (s2 != s && b1e && b1e[0] == '1') ? (size_t)120 * 1024 : GT_SMEM_BYTES;
          bool cpass[2] = {false, false};
          bool bulk = false;
          int cnt_o = cnt;
@@ -514,7 +518,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                if (split) {
                   TileBatch ub{d_fr, d_upd, cnt_o};
                   ProfScope ps(nt, KC_UPDATE, s2);
-                  k_gemm_batched<<<gemm_grid(7, upd_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, ub, 7, slot, IB, nullptr, 0, 0, 1);
+                  k_gemm_batched<<<gemm_grid(7, upd_prefix[cnt_o]), GT_THREADS, bulk_smem, s2>>>(T, ub, 7, slot, IB, nullptr, 0, 0, 1);
                   ++launches;
                   CU_TRY(cudaEventRecord(nt->ev_bulk, s2));
                   bulk = true;
@@ -522,7 +526,7 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                if (con_prefix[cnt_o] > 0) {
                   TileBatch cb{d_fr, d_con, cnt_o};
                   ProfScope ps(nt, KC_CONTRIB, s2);
-                  k_gemm_batched<<<gemm_grid(6, con_prefix[cnt_o]), GT_THREADS, GT_SMEM_BYTES, s2>>>(T, cb, 6, slot, IB, nullptr, 0, 0, 1);
+                  k_gemm_batched<<<gemm_grid(6, con_prefix[cnt_o]), GT_THREADS, bulk_smem, s2>>>(T, cb, 6, slot, IB, nullptr, 0, 0, 1);
                   ++launches;
                }
                if (s2 != s) {
