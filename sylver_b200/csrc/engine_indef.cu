@@ -256,7 +256,12 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    }
    // SYLVER_B200_APTP_LEGACY=1: round-1 launch sequence (apply / finish / swap as separate launches,
    // one contribution update after the last panel) for A/B runs
-   const bool legacy = getenv("SYLVER_B200_APTP_LEGACY") && getenv("SYLVER_B200_APTP_LEGACY")[0] == '1';
+   // Rank threads of the in-process fabric share ONE device: kernels whose CTAs wait for each other
+   // (k_block_column32, k_tpp_multi) assume that the launch they belong to gets the GPU's CTA slots
+   // in order, which several concurrently launching ranks break -- the launch sequence without
+   // device-side rendezvous is used there.
+   const bool shared_device = comm().fabric != nullptr;
+   const bool legacy = shared_device || (getenv("SYLVER_B200_APTP_LEGACY") && getenv("SYLVER_B200_APTP_LEGACY")[0] == '1');
    long launches = 0;
    for (auto& c : nt->chunks) c.used = 0;
    if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
@@ -541,7 +546,15 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
          // ---- second pass (TPP) on failed columns, contribution blocks, statistics ----
          {
             ProfScope ps(nt, KC_ZERO);
-            k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
+            // G CTAs per front while the whole launch stays resident (the group barrier spins);
+            // SYLVER_B200_TPP_G=1 selects the single-CTA kernel
+            const char* tge = getenv("SYLVER_B200_TPP_G");
+            const int gmax = tge ? std::max(1, std::min(TPP_GMAX, atoi(tge))) : TPP_GMAX;
+            const int G = shared_device ? 1 : std::max(1, std::min(gmax, 128 / std::max(cnt, 1)));
+            if (G > 1)
+               k_tpp_multi<<<cnt * G, TPP_THREADS, 0, s>>>(T, d_fr, d_diag, u, small, tpp_everywhere ? 0 : 1, G);
+            else
+               k_tpp<<<cnt, TPP_THREADS, 0, s>>>(T, d_fr, u, small, tpp_everywhere ? 0 : 1);
             ++launches;
          }
          if (con_prefix[cnt] > 0) {

@@ -915,6 +915,348 @@ static __global__ void __launch_bounds__(TPP_THREADS) k_tpp(DevTree T, const int
 }
 
 // ---------------------------------------------------------------------------
+// k_tpp_multi: the same second pass with G CTAs per front.  The pivot search is sequential, but
+// every step of it is a reduction over, or an update of, all rows of the front: a front with a
+// few thousand failed columns spends O(m F^2) flops here, far too much for one SM.  The G CTAs
+// of a front take rows (and, in the row-wise scans, columns) g, g + G, ... in chunks of the CTA
+// width, exchange partial maxima through a small per-front scratch and meet at a front-wide
+// barrier (same dispatch-order argument as k_block_column32: G <= 16 consecutive CTAs).  All CTAs
+// evaluate the decisions redundantly on the same values, so they take the same branches; the
+// tests and the arithmetic are those of k_tpp (ldlt_tpp_factor).
+// The search itself is batched: the reference examines the candidates p = nelim+1, nelim+2, ...
+// one after the other until one can be pivoted, and a rejected candidate changes nothing -- so
+// the G CTAs examine G consecutive candidates at once, one each, and the smallest p that can be
+// pivoted wins: the same pivot sequence, found in 1/G of the rounds.
+// ---------------------------------------------------------------------------
+constexpr int TPP_GMAX = 64;    // CTAs per front at most
+struct TppScratch {
+   double part[2][TPP_GMAX][5];      // [round parity][CTA][value]: partial maxima / a candidate's verdict
+};
+static_assert(sizeof(TppScratch) <= sizeof(DiagScratch), "TPP scratch lives in the diagonal-block scratch");
+
+struct TppGroup {
+   FrontState* st;
+   TppScratch* sc;
+   int g, G;
+   int epoch;                  // barriers passed so far
+   int round;                  // reduction rounds so far
+};
+
+__device__ __forceinline__ void tpp_barrier(TppGroup& tg) {
+   __syncthreads();
+   ++tg.epoch;
+   if (tg.G > 1 && threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&tg.st->arrive, 1);
+      while (atomicAdd(&tg.st->arrive, 0) < tg.G * tg.epoch) __nanosleep(32);
+      __threadfence();
+   }
+   __syncthreads();
+}
+
+// CTA-wide max of up to 4 values per thread, then across the front's CTAs; result in v[0..nv)
+template <int NV>
+__device__ __forceinline__ void tpp_allmax(TppGroup& tg, double (&v)[NV], double* red) {
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+   for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+   __syncthreads();
+   if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < NV; ++k) {
+      double r = red[k];
+      for (int i = 1; i < TPP_THREADS / 32; ++i) r = fmax(r, red[i * NV + k]);
+      v[k] = r;
+   }
+   if (tg.G == 1) return;
+   const int par = tg.round & 1;
+   ++tg.round;
+   if (threadIdx.x == 0)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) tg.sc->part[par][tg.g][k] = v[k];
+   tpp_barrier(tg);
+#pragma unroll
+   for (int k = 0; k < NV; ++k) {
+      double r = 0.0;
+      for (int i = 0; i < tg.G; ++i) r = fmax(r, __ldcg(&tg.sc->part[par][i][k]));
+      v[k] = r;
+   }
+}
+
+// distributed symmetric swap of candidate variables i < j (cta_sym_swap split over the group)
+__device__ __forceinline__ void tpp_sym_swap(TppGroup& tg, double* Lf, double* Wf, int* perm, int ldl, int m, int n,
+                                             int nleft, int i, int j, int wfirst) {
+   if (i == j) return;
+   if (i > j) { const int x = i; i = j; j = x; }
+   const int t0 = tg.g * TPP_THREADS + threadIdx.x, nt = tg.G * TPP_THREADS;
+   for (int c = t0; c < i; c += nt) {
+      double* col = Lf + (size_t)c * ldl;
+      const double x = __ldcg(col + i); col[i] = __ldcg(col + j); col[j] = x;
+      if (c < nleft && c >= wfirst) {
+         double* wc = Wf + (size_t)c * ldl;
+         const double y = __ldcg(wc + i); wc[i] = __ldcg(wc + j); wc[j] = y;
+      }
+   }
+   for (int k = i + 1 + t0; k < j; k += nt) {
+      double* p1 = Lf + (size_t)i * ldl + k;
+      double* p2 = Lf + (size_t)k * ldl + j;
+      const double x = __ldcg(p1); *p1 = __ldcg(p2); *p2 = x;
+   }
+   if (j < n) {
+      for (int r = j + 1 + t0; r < m; r += nt) {
+         double* p1 = Lf + (size_t)i * ldl + r;
+         double* p2 = Lf + (size_t)j * ldl + r;
+         const double x = __ldcg(p1); *p1 = __ldcg(p2); *p2 = x;
+      }
+   }
+   if (t0 == 0) {
+      double* p1 = Lf + (size_t)i * ldl + i;
+      double* p2 = Lf + (size_t)j * ldl + j;
+      const double x = __ldcg(p1); *p1 = __ldcg(p2); *p2 = x;
+      const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+   }
+   tpp_barrier(tg);
+}
+
+static __global__ void __launch_bounds__(TPP_THREADS) k_tpp_multi(DevTree T, const int* __restrict__ fronts,
+                                                                  DiagScratch* __restrict__ scratch, double u, double small,
+                                                                  int force_root_only, int G) {
+   __shared__ double red[(TPP_THREADS / 32) * 4];
+   __shared__ int s_idx;
+   const int fi = blockIdx.x / G;
+   const int f = fronts[fi];
+   FrontState& st = T.state[f];
+   const int m = T.m[f], n = T.n[f], ldl = T.ldl[f];
+   int nelim = st.p0;
+   TppGroup tg{&st, reinterpret_cast<TppScratch*>(&scratch[fi]), (int)(blockIdx.x % G), G, 0, 0};
+   const bool skip = nelim >= n || (force_root_only && m != n);
+   if (skip) {
+      // every CTA of the front takes this branch (same state); only one writes
+      if (tg.g == 0 && threadIdx.x == 0) { st.nelim1 = nelim; st.nelim = nelim; }
+      return;
+   }
+   double* Lf = T.L + T.loff[f];
+   double* Wf = T.W + T.woff[f];
+   double* D = T.D + T.doff[f];
+   int* perm = T.perm + T.permoff[f];
+   const int t0 = tg.g * TPP_THREADS + threadIdx.x, nt = G * TPP_THREADS;
+   const int nelim_in = nelim;
+   // max |a(idx, c)|, nelim <= c < idx (row part) and |a(r, idx)|, r0 <= r < m (column part), without `ex`
+   auto scan = [&](int idx, int r0, int ex) -> double {
+      double best = 0.0;
+      for (int c = nelim + t0; c < idx; c += nt)
+         if (c != ex) best = fmax(best, fabs(__ldcg(Lf + (size_t)c * ldl + idx)));
+      for (int r = r0 + t0; r < m; r += nt)
+         if (r != ex) best = fmax(best, fabs(__ldcg(Lf + (size_t)idx * ldl + r)));
+      return best;
+   };
+   // the same scan by this CTA alone (its candidate's trial)
+   auto scan1 = [&](int idx, int r0, int ex) -> double {
+      double best = 0.0;
+      for (int c = nelim + threadIdx.x; c < idx; c += TPP_THREADS)
+         if (c != ex) best = fmax(best, fabs(__ldcg(Lf + (size_t)c * ldl + idx)));
+      for (int r = r0 + threadIdx.x; r < m; r += TPP_THREADS)
+         if (r != ex) best = fmax(best, fabs(__ldcg(Lf + (size_t)idx * ldl + r)));
+      return best;
+   };
+   auto cta_max2 = [&](double (&v)[2], double* rd) {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+      __syncthreads();
+      if (lane == 0) { rd[warp * 2] = v[0]; rd[warp * 2 + 1] = v[1]; }
+      __syncthreads();
+      double r0 = rd[0], r1 = rd[1];
+      for (int i = 1; i < TPP_THREADS / 32; ++i) { r0 = fmax(r0, rd[2 * i]); r1 = fmax(r1, rd[2 * i + 1]); }
+      v[0] = r0; v[1] = r1;
+   };
+   auto zero_pivot = [&]() {
+      for (int r = nelim + t0; r < m; r += nt) {
+         Lf[(size_t)nelim * ldl + r] = 0.0;
+         Wf[(size_t)nelim * ldl + r] = 0.0;
+      }
+      if (t0 == 0) { D[2 * nelim] = 0.0; D[2 * nelim + 1] = 0.0; }
+      tpp_barrier(tg);
+      ++nelim;
+   };
+   auto elim_1x1 = [&]() {      // pivot sits at (nelim, nelim)
+      const double d11 = 1.0 / __ldcg(Lf + (size_t)nelim * ldl + nelim);
+      tpp_barrier(tg);          // everyone has read the diagonal before it becomes 1
+      double* a1 = Lf + (size_t)nelim * ldl;
+      double* w1 = Wf + (size_t)nelim * ldl;
+      for (int r = nelim + 1 + t0; r < m; r += nt) {
+         const double v = __ldcg(a1 + r);
+         w1[r] = v;
+         a1[r] = v * d11;
+      }
+      if (t0 == 0) { a1[nelim] = 1.0; D[2 * nelim] = d11; D[2 * nelim + 1] = 0.0; }
+      tpp_barrier(tg);
+      const int nc = n - nelim - 1;
+      for (int c = 0; c < nc; ++c) {
+         const int cc = nelim + 1 + c;
+         const double wc = __ldcg(w1 + cc);
+         double* ac = Lf + (size_t)cc * ldl;
+         for (int r = cc + t0; r < m; r += nt) ac[r] = __ldcg(ac + r) - __ldcg(a1 + r) * wc;
+      }
+      tpp_barrier(tg);
+      nelim += 1;
+   };
+   auto elim_2x2 = [&](double d11, double d21, double d22) {
+      double* a1 = Lf + (size_t)nelim * ldl;
+      double* a2 = Lf + (size_t)(nelim + 1) * ldl;
+      double* w1 = Wf + (size_t)nelim * ldl;
+      double* w2 = Wf + (size_t)(nelim + 1) * ldl;
+      for (int r = nelim + 2 + t0; r < m; r += nt) {
+         const double v1 = __ldcg(a1 + r), v2 = __ldcg(a2 + r);
+         w1[r] = v1; w2[r] = v2;
+         a1[r] = d11 * v1 + d21 * v2;
+         a2[r] = d21 * v1 + d22 * v2;
+      }
+      if (t0 == 0) {
+         w1[nelim + 1] = __ldcg(a1 + nelim + 1);
+         a1[nelim] = 1.0; a1[nelim + 1] = 0.0; a2[nelim + 1] = 1.0;
+         D[2 * nelim] = d11; D[2 * nelim + 1] = d21; D[2 * nelim + 2] = INFINITY; D[2 * nelim + 3] = d22;
+      }
+      tpp_barrier(tg);
+      const int nc = n - nelim - 2;
+      for (int c = 0; c < nc; ++c) {
+         const int cc = nelim + 2 + c;
+         const double wc1 = __ldcg(w1 + cc), wc2 = __ldcg(w2 + cc);
+         double* ac = Lf + (size_t)cc * ldl;
+         for (int r = cc + t0; r < m; r += nt) ac[r] = __ldcg(ac + r) - (__ldcg(a1 + r) * wc1 + __ldcg(a2 + r) * wc2);
+      }
+      tpp_barrier(tg);
+      nelim += 2;
+   };
+   while (nelim < n) {
+      {
+         double v[1] = {scan(nelim, nelim, -1)};      // check_col_small(nelim)
+         tpp_allmax<1>(tg, v, red);
+         if (v[0] < small) { zero_pivot(); continue; }
+      }
+      bool done = false;
+      for (int base = nelim + 1; base < n && !done; base += G) {
+         // ---- this CTA's candidate: the whole trial with CTA-local reductions ----
+         const int p = base + tg.g;
+         int verdict = 0, t = 0;      // 0 rejected, 1 zero column, 2 2x2 pivot (t, p), 3 1x1 pivot p
+         double d11 = 0, d21 = 0, d22 = 0;
+         if (p < n) {
+            double bv = -1.0;
+            int bi = p;
+            for (int c = nelim + threadIdx.x; c < p; c += TPP_THREADS) {
+               const double x = fabs(__ldcg(Lf + (size_t)c * ldl + p));
+               if (x > bv) { bv = x; bi = c; }
+            }
+            double v[2] = {scan1(p, p, -1), bv};
+            cta_max2(v, red);
+            if (v[0] < small) {
+               verdict = 1;
+            } else {
+               if (threadIdx.x == 0) s_idx = n;
+               __syncthreads();
+               if (bv == v[1]) atomicMin(&s_idx, bi);
+               __syncthreads();
+               t = s_idx;
+               double mm[2] = {scan1(t, t + 1, p), scan1(p, p + 1, t)};      // maxt, maxp (tpp_rc_max)
+               cta_max2(mm, red);
+               const double maxt = mm[0];
+               double maxp = mm[1];
+               // test_2x2 (ldlt_tpp.cxx:89-119)
+               const double a11 = __ldcg(Lf + (size_t)t * ldl + t), a21 = __ldcg(Lf + (size_t)t * ldl + p),
+                            a22 = __ldcg(Lf + (size_t)p * ldl + p);
+               const double maxpiv = fmax(fabs(a11), fmax(fabs(a21), fabs(a22)));
+               if (maxpiv >= small) {
+                  const double detscale = 1 / maxpiv;
+                  const double detpiv0 = (a11 * detscale) * a22;
+                  const double detpiv1 = (a21 * detscale) * a21;
+                  const double detpiv = detpiv0 - detpiv1;
+                  if (!(fabs(detpiv) < fmax(small, fmax(fabs(detpiv0 / 2), fabs(detpiv1 / 2))))) {
+                     d11 = (a22 * detscale) / detpiv;
+                     d21 = (-a21 * detscale) / detpiv;
+                     d22 = (a11 * detscale) / detpiv;
+                     if (fmax(maxp, maxt) < small) verdict = 2;
+                     else {
+                        const double x1 = fabs(d11) * maxt + fabs(d21) * maxp;
+                        const double x2 = fabs(d21) * maxt + fabs(d22) * maxp;
+                        if (u * fmax(x1, x2) < 1.0) verdict = 2;
+                     }
+                  }
+               }
+               if (verdict == 0) {
+                  maxp = fmax(maxp, fabs(a21));
+                  if (fabs(a22) >= u * maxp) verdict = 3;
+               }
+            }
+         }
+         // ---- publish, meet, take the smallest candidate that can be pivoted ----
+         const int par = tg.round & 1;
+         ++tg.round;
+         if (threadIdx.x == 0) {
+            double* o = tg.sc->part[par][tg.g];
+            o[0] = (double)verdict; o[1] = (double)t; o[2] = d11; o[3] = d21; o[4] = d22;
+         }
+         tpp_barrier(tg);
+         int wg = -1;
+         for (int i = 0; i < G && base + i < n; ++i)
+            if (__ldcg(&tg.sc->part[par][i][0]) != 0.0) { wg = i; break; }
+         if (wg < 0) continue;
+         const int wp = base + wg;
+         const int wv = (int)__ldcg(&tg.sc->part[par][wg][0]);
+         const int wt = (int)__ldcg(&tg.sc->part[par][wg][1]);
+         const double e11 = __ldcg(&tg.sc->part[par][wg][2]), e21 = __ldcg(&tg.sc->part[par][wg][3]),
+                      e22 = __ldcg(&tg.sc->part[par][wg][4]);
+         if (wv == 1) {
+            tpp_sym_swap(tg, Lf, Wf, perm, ldl, m, n, nelim, nelim, wp, nelim);
+            zero_pivot();
+         } else if (wv == 2) {
+            tpp_sym_swap(tg, Lf, Wf, perm, ldl, m, n, nelim, nelim, wt, nelim);
+            tpp_sym_swap(tg, Lf, Wf, perm, ldl, m, n, nelim, nelim + 1, wp, nelim);
+            elim_2x2(e11, e21, e22);
+         } else {
+            tpp_sym_swap(tg, Lf, Wf, perm, ldl, m, n, nelim, nelim, wp, nelim);
+            elim_1x1();
+         }
+         done = true;
+      }
+      if (!done) {
+         // last resort: 1x1 on column nelim
+         double v[1] = {scan(nelim, nelim + 1, -1)};
+         tpp_allmax<1>(tg, v, red);
+         const double dd = __ldcg(Lf + (size_t)nelim * ldl + nelim);
+         if (fabs(dd) >= u * v[0]) {
+            elim_1x1();
+         } else {
+            break;       // out of pivots: the rest is delayed
+         }
+      }
+   }
+   tpp_barrier(tg);
+   if (threadIdx.x == 0) {
+      if (tg.g == 0) {
+         st.nelim1 = nelim_in;
+         st.nelim = nelim;
+         st.p0 = nelim;
+      }
+      // the barrier counter may only be cleared once every CTA has LEFT the last barrier (a CTA
+      // still spinning on it would never see the target again): the last one out clears it
+      if (G > 1) {
+         __threadfence();
+         if (atomicAdd(&st.done, 1) == G - 1) {
+            st.arrive = 0;
+            st.done = 0;
+         }
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------
 // k_front_stats: inertia and pivot statistics of a level (src/NumericTree.hxx:150-179;
 // factor_failed.hxx:64,118-127).  One thread per front.
 // stats: [0] num_delay [1] num_neg [2] num_two [3] num_zero [4] not_first_pass [5] not_second_pass
