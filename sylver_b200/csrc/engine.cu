@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -453,6 +454,7 @@ static void plan_split(NumericTree* nt, bool device) {
    nt->crecvs.assign(st->nlevels, {});
    std::vector<int> split_fronts;
    size_t stage = 0;
+   long pair_seq = 0;
    for (int l = 0; l < st->nlevels; ++l) {
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
@@ -477,8 +479,9 @@ static void plan_split(NumericTree* nt, bool device) {
          auto emit = [&](int src, long off, size_t count) {
             for (int d = d0; d < d1; ++d) {
                if (d == src) continue;
-               if (src == me) nt->csends[l].push_back(Piece{f, d, off, count});
-               else if (d == me) nt->crecvs[l].push_back(Piece{f, src, off, count});
+               const long seq = pair_seq++;      // counted on every rank, whether it takes part or not
+               if (src == me) nt->csends[l].push_back(Piece{f, d, off, count, seq});
+               else if (d == me) nt->crecvs[l].push_back(Piece{f, src, off, count, seq});
             }
          };
          const long ldc = nt->ldc[f];
@@ -812,16 +815,35 @@ static void issue_exchange(NumericTree* nt, int l, double* base, const std::vect
 }
 
 // Contribution pieces whose destination ranks differ from their holder (see plan_split).
+//
+// The pieces of a level are NOT put into one NCCL group: a level of lap7_150 on 8 GPUs has ~1000
+// point-to-point operations per rank, NCCL cuts such a group into several kernels at points that
+// differ from rank to rank (each rank has a different list), and a kernel that waits for a
+// message its peer only posts in a LATER kernel never returns -- the 8-GPU hang of round 1.
+// Every (piece, destination) pair carries its position `seq` in the enumeration all ranks share;
+// pairs are grouped by seq / EX_CHUNK, so a send and its receive always sit in the same, small
+// group on both sides and the groups follow each other in the same order everywhere.
+constexpr long EX_CHUNK = 48;
 static void issue_contrib_exchange(NumericTree* nt, int l) {
    if (nt->world <= 1) return;
    const auto& sd = nt->csends[l];
    const auto& rv = nt->crecvs[l];
    if (sd.empty() && rv.empty()) return;
-   int rc = comm_group_start();
-   for (const Piece& x : sd) rc |= comm_send(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream);
-   for (const Piece& x : rv) rc |= comm_recv(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream);
-   rc |= comm_group_end();
-   if (rc) throw CudaFailure{-52};
+   size_t is = 0, ir = 0;      // both lists are in increasing seq order
+   while (is < sd.size() || ir < rv.size()) {
+      const long next = std::min(is < sd.size() ? sd[is].seq : LONG_MAX, ir < rv.size() ? rv[ir].seq : LONG_MAX);
+      const long chunk = next / EX_CHUNK;
+      int rc = comm_group_start();
+      while (is < sd.size() || ir < rv.size()) {
+         const bool take_send = is < sd.size() && (ir >= rv.size() || sd[is].seq < rv[ir].seq);
+         const Piece& x = take_send ? sd[is] : rv[ir];
+         if (x.seq / EX_CHUNK != chunk) break;
+         if (take_send) { rc |= comm_send(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream); ++is; }
+         else { rc |= comm_recv(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream); ++ir; }
+      }
+      rc |= comm_group_end();
+      if (rc) throw CudaFailure{-52};
+   }
 }
 
 // One front split over a rank group (top of the tree).  Block column j of the

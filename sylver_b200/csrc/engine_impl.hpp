@@ -126,6 +126,7 @@ struct Piece {
    int f, peer;
    long off;
    size_t count;
+   long seq;      // position of this (piece, destination) pair in the enumeration all ranks share
 };
 // A front whose block columns are dealt round-robin to the ranks [g0, g0 + P) (top of the
 // tree): this rank is member q; panels travel by broadcast on sub-communicator gid.
