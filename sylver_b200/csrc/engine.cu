@@ -53,6 +53,12 @@ SymbolicTree::~SymbolicTree() {
 }
 
 // Host-only copies needed again at upload time
+// Point-to-point operations of one rank in one NCCL group (contribution pieces).  Groups of ~400
+// per rank (lap27_100 on 8 GPUs) have always worked, ~800-1050 (lap7_150) hang; smaller groups
+// cost time (lap27_100 on 8 GPUs: 90 ms per step with one group per level, 102 ms with groups of
+// 128, 105 ms with groups of 48 -- the transfers of a group overlap, consecutive groups do not).
+constexpr int EX_MAX_OPS = 400;
+
 struct SymbolicExtra {
    std::vector<long> rptr1;   // 1-based rptr as given
    std::vector<long> nlist;   // (src,dest) pairs as given
@@ -455,7 +461,10 @@ static void plan_split(NumericTree* nt, bool device) {
    std::vector<int> split_fronts;
    size_t stage = 0;
    long pair_seq = 0;
+   std::vector<int> ex_count(std::max(nt->world, 1), 0);
    for (int l = 0; l < st->nlevels; ++l) {
+      ++pair_seq;      // groups never span levels
+      std::fill(ex_count.begin(), ex_count.end(), 0);
       for (int i = st->level_ptr[l]; i < st->level_ptr[l + 1]; ++i) {
          const int f = st->level_nodes[i];
          if (nt->splitP[f] > 1) {
@@ -479,7 +488,15 @@ static void plan_split(NumericTree* nt, bool device) {
          auto emit = [&](int src, long off, size_t count) {
             for (int d = d0; d < d1; ++d) {
                if (d == src) continue;
-               const long seq = pair_seq++;      // counted on every rank, whether it takes part or not
+               // group id, computed identically on every rank (whether it takes part or not): a new
+               // group starts when either end of the pair already has EX_MAX_OPS operations in it
+               if (ex_count[src] >= EX_MAX_OPS || ex_count[d] >= EX_MAX_OPS) {
+                  ++pair_seq;
+                  std::fill(ex_count.begin(), ex_count.end(), 0);
+               }
+               ++ex_count[src];
+               ++ex_count[d];
+               const long seq = pair_seq;
                if (src == me) nt->csends[l].push_back(Piece{f, d, off, count, seq});
                else if (d == me) nt->crecvs[l].push_back(Piece{f, src, off, count, seq});
             }
@@ -817,13 +834,13 @@ static void issue_exchange(NumericTree* nt, int l, double* base, const std::vect
 // Contribution pieces whose destination ranks differ from their holder (see plan_split).
 //
 // The pieces of a level are NOT put into one NCCL group: a level of lap7_150 on 8 GPUs has ~1000
-// point-to-point operations per rank, NCCL cuts such a group into several kernels at points that
-// differ from rank to rank (each rank has a different list), and a kernel that waits for a
-// message its peer only posts in a LATER kernel never returns -- the 8-GPU hang of round 1.
-// Every (piece, destination) pair carries its position `seq` in the enumeration all ranks share;
-// pairs are grouped by seq / EX_CHUNK, so a send and its receive always sit in the same, small
-// group on both sides and the groups follow each other in the same order everywhere.
-constexpr long EX_CHUNK = 48;
+// point-to-point operations per rank (lap27_100: ~400, which works), NCCL cuts such a group into
+// several kernels at points that differ from rank to rank (each rank has a different list), and a
+// kernel that waits for a message its peer only posts in a LATER kernel never returns -- the
+// 8-GPU hang of round 1.  plan_split assigns every (piece, destination) pair a group id `seq`,
+// the same on all ranks, such that no rank has more than EX_MAX_OPS operations in a group: a send
+// and its receive always sit in the same, bounded group on both sides, and the groups follow each
+// other in the same order everywhere.
 static void issue_contrib_exchange(NumericTree* nt, int l) {
    if (nt->world <= 1) return;
    const auto& sd = nt->csends[l];
@@ -831,13 +848,12 @@ static void issue_contrib_exchange(NumericTree* nt, int l) {
    if (sd.empty() && rv.empty()) return;
    size_t is = 0, ir = 0;      // both lists are in increasing seq order
    while (is < sd.size() || ir < rv.size()) {
-      const long next = std::min(is < sd.size() ? sd[is].seq : LONG_MAX, ir < rv.size() ? rv[ir].seq : LONG_MAX);
-      const long chunk = next / EX_CHUNK;
+      const long chunk = std::min(is < sd.size() ? sd[is].seq : LONG_MAX, ir < rv.size() ? rv[ir].seq : LONG_MAX);
       int rc = comm_group_start();
       while (is < sd.size() || ir < rv.size()) {
-         const bool take_send = is < sd.size() && (ir >= rv.size() || sd[is].seq < rv[ir].seq);
+         const bool take_send = is < sd.size() && (ir >= rv.size() || sd[is].seq <= rv[ir].seq);
          const Piece& x = take_send ? sd[is] : rv[ir];
-         if (x.seq / EX_CHUNK != chunk) break;
+         if (x.seq != chunk) break;
          if (take_send) { rc |= comm_send(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream); ++is; }
          else { rc |= comm_recv(nt->d_C + nt->coff[x.f] + x.off, x.count, x.peer, nt->stream); ++ir; }
       }
