@@ -82,7 +82,9 @@ typedef struct {
    double small;              /* 1e-20 */
    double u;                  /* 0.01 */
    long small_subtree_threshold;
-   int nb;                    /* 256 */
+   int nb;                    /* default 256; accepted, not used: the engine's blocking is fixed by its kernels
+                               * (128-column Cholesky block columns, APTP outer panels of 256 with 32-column
+                               * inner blocks = the reference's nb / ib) */
    int cpu_topology;
    bool action;               /* true: continue on singularity with a warning */
    bool use_gpu;
@@ -160,7 +162,7 @@ typedef struct {
    double u;
    double multiplier;
    long small_subtree_threshold;
-   int nb;
+   int nb;                    /* accepted, not used (see sylver_options_t.nb) */
    int pivot_method;
    int failed_pivot_method;
    int cpu_topology;
