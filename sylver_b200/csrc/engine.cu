@@ -1338,6 +1338,7 @@ void numeric_tree_destroy(NumericTree* nt) {
    cudaFree(nt->d_W); cudaFree(nt->d_aval); cudaFree(nt->d_scaling); cudaFree(nt->d_fail);
    cudaFree(nt->d_prefix); cudaFree(nt->d_asm_work); cudaFree(nt->d_xw); cudaFree(nt->d_xwoff);
    cudaFree(nt->d_child_ptr); cudaFree(nt->d_child_list);
+   cudaFree(nt->d_solve_bar); cudaFree(nt->d_solve_part); cudaFree(nt->d_xrhs);
    cudaFree(nt->d_splitP); cudaFree(nt->d_splitQ); cudaFree(nt->d_scat_owner); cudaFree(nt->d_fac_nodes);
    cudaFree(nt->d_split_fronts); cudaFree(nt->d_zero); cudaFree(nt->d_stage); cudaFree(nt->d_Wsplit);
    cudaFree(nt->d_lvl_nodes); cudaFree(nt->d_owner); cudaFree(nt->d_all_nodes); cudaFree(nt->d_xbuf); cudaFree(nt->d_xpack_off);
@@ -1524,6 +1525,11 @@ static void ensure_solve_workspace(NumericTree* nt) {
    nt->d_xwoff = dev_upload(nt->xwoff);
    if (!nt->d_child_ptr) nt->d_child_ptr = dev_upload(st->child_ptr);
    if (!nt->d_child_list) nt->d_child_list = dev_upload(st->child_list);
+   if (!nt->d_solve_bar) {
+      // multi-CTA solve kernels: one barrier counter per front slot of a launch, partial sums
+      CU_TRY(cudaMalloc(&nt->d_solve_bar, 128 * sizeof(int)));
+      CU_TRY(cudaMalloc(&nt->d_solve_part, (size_t)128 * SOLVE_BW * sizeof(double)));
+   }
    if (nt->world > 1 && !nt->posdef && !nt->d_xbuf) {
       // replicated-x delta exchange (k_delta_pack): previous x + (value, changed) pairs
       nt->xbuf_cap = 3 * (size_t)std::max(st->n, 1);
@@ -1561,8 +1567,15 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
          cudaGetLastError();
       double* dx = x;
       if (!on_dev) {
-         CU_TRY(cudaMalloc(&dx, (size_t)ldx * nrhs * sizeof(double)));
-         CU_TRY(cudaMemcpyAsync(dx, x, (size_t)ldx * nrhs * sizeof(double), cudaMemcpyHostToDevice, nt->stream));
+         const size_t need = (size_t)ldx * nrhs;
+         if (need > nt->xrhs_cap) {
+            if (nt->d_xrhs) CU_TRY(cudaFree(nt->d_xrhs));
+            nt->d_xrhs = nullptr;
+            CU_TRY(cudaMalloc(&nt->d_xrhs, need * sizeof(double)));
+            nt->xrhs_cap = need;
+         }
+         dx = nt->d_xrhs;
+         CU_TRY(cudaMemcpyAsync(dx, x, need * sizeof(double), cudaMemcpyHostToDevice, nt->stream));
       }
       SolveArgs a{};
       a.T = nt->T;
@@ -1597,10 +1610,36 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
          if (delta) CU_TRY(cudaMemcpyAsync(xprev, a.x, nn * sizeof(double), cudaMemcpyDeviceToDevice, nt->stream));
          const int* lptr = multi ? nt->lvl_ptr.data() : st->level_ptr.data();
          const int* d_nodes = multi ? nt->d_lvl_nodes : st->d_level_nodes;
+         // levels with few (large) fronts: G CTAs per front (k_solve_*_multi), the whole launch
+         // resident; the shared-device test fabric keeps one CTA per front (concurrent rank threads)
+         const char* sge = getenv("SYLVER_B200_SOLVE_G");
+         const int gcap = sge ? std::max(1, std::min(SOLVE_GMAX, atoi(sge))) : SOLVE_GMAX;
+         auto group_size = [&](int count) {
+            if (comm().fabric || count <= 0 || count > 32) return 1;
+            return std::max(1, std::min(gcap, 128 / count));
+         };
+         auto launch_fwd = [&](const int* d_list, int count) {
+            const int G = group_size(count);
+            if (G > 1) {
+               CU_TRY(cudaMemsetAsync(nt->d_solve_bar, 0, count * sizeof(int), nt->stream));
+               k_solve_fwd_multi<<<count * G, SOLVE_THREADS, 0, nt->stream>>>(a, d_list, G, nt->d_solve_bar);
+            } else {
+               k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_list);
+            }
+         };
+         auto launch_bwd = [&](const int* d_list, int count) {
+            const int G = group_size(count);
+            if (G > 1) {
+               CU_TRY(cudaMemsetAsync(nt->d_solve_bar, 0, count * sizeof(int), nt->stream));
+               k_solve_bwd_multi<<<count * G, SOLVE_THREADS, 0, nt->stream>>>(a, d_list, G, nt->d_solve_bar, nt->d_solve_part);
+            } else {
+               k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_list);
+            }
+         };
          if (do_fwd) {
             for (int l = 0; l < st->nlevels; ++l) {
                const int first = lptr[l], count = lptr[l + 1] - first;
-               if (count > 0) k_solve_fwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
+               if (count > 0) launch_fwd(d_nodes + first, count);
                // update vectors of fronts whose parent lives on another GPU (rows >= n of xw)
                if (multi) issue_exchange(nt, l, nt->d_xw, nt->xwoff, &nt->n);
                if (delta) sync_x();
@@ -1619,7 +1658,7 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
          if (do_bwd)
             for (int l = st->nlevels - 1; l >= 0; --l) {
                const int first = lptr[l], count = lptr[l + 1] - first;
-               if (count > 0) k_solve_bwd<<<count, SOLVE_THREADS, 0, nt->stream>>>(a, d_nodes + first);
+               if (count > 0) launch_bwd(d_nodes + first, count);
                if (delta) sync_x();
                if (multi && !delta) {
                   // broadcast the entries solved at this level: pack (zeros for fronts of other
@@ -1641,7 +1680,6 @@ int numeric_tree_solve(const NumericTree* cnt, int job, int nrhs, double* x, int
       if (!on_dev) {
          CU_TRY(cudaMemcpyAsync(x, dx, (size_t)ldx * nrhs * sizeof(double), cudaMemcpyDeviceToHost, nt->stream));
          CU_TRY(cudaStreamSynchronize(nt->stream));
-         CU_TRY(cudaFree(dx));
       } else {
          CU_TRY(cudaStreamSynchronize(nt->stream));
       }

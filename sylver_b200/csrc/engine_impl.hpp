@@ -185,6 +185,9 @@ struct NumericTree {
    long* d_xwoff = nullptr;
    std::vector<long> xwoff;
    int* d_child_ptr = nullptr; int* d_child_list = nullptr;
+   int* d_solve_bar = nullptr;           // multi-CTA solve: barrier counters (one per front slot of a launch)
+   double* d_solve_part = nullptr;       //                  partial dot products [slot][G][128]
+   double* d_xrhs = nullptr; size_t xrhs_cap = 0;   // device copy of a host right-hand side (kept between calls)
    // ---- multi-GPU (one process per GPU): fronts owned by this rank, exchanges per level ----
    int rank = 0, world = 1;
    std::vector<int> owner;               // rank owning each front (partition_tree)
