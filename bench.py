@@ -449,7 +449,9 @@ def ours(a):
             "flops_per_launch": g_fl / max(g_nl, 1), "avg_launch_ms": g_ms / max(g_nl, 1),
             "launches": g_nl,
             "share_of_step": g_ms / ms_step,
-            "share_note": "kernel time of the profiled (un-graphed, event-bracketed) pass / the timed step",
+            "share_note": "kernel time of the profiled pass (un-graphed; the same launches as the timed step, each bracketed "
+                          "by CUDA events, the look-ahead chain issued on the main stream so that a bracket holds the "
+                          "kernel's own time) / the timed step",
             "per_mode": {k: {"tflops": fl[k] / max(ms[k], 1e-9) / 1e9, "frac": fl[k] / max(ms[k], 1e-9) / 1e9 / peak}
                          for k in ("trsm", "update", "contrib")},
             "traffic": traffic}

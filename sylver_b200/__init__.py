@@ -389,7 +389,8 @@ def plan_levels(solver: "Solver", rank: int = 0, world: int = 1):
 
 def plan_split(solver: "Solver", rank: int, world: int):
     """Host-only positive definite plan of `rank` among `world` ranks (sylver_b200_plan_split):
-    (summary dict, pieces array of rows (level, front, peer, offset, count, direction))."""
+    (summary dict, pieces array of rows (level, front, peer, offset, count, direction, group)) --
+    group = id of the NCCL group the operation is issued in (identical on both sides of a pair)."""
     out = np.zeros(8, dtype=np.int64)
     cnt = lib().sylver_b200_plan_split(solver.akeep, rank, world, _ptr(out), 0, None)
     if cnt < 0:
@@ -397,7 +398,9 @@ def plan_split(solver: "Solver", rank: int, world: int):
     pieces = np.zeros((max(cnt, 1), 6), dtype=np.int64)
     lib().sylver_b200_plan_split(solver.akeep, rank, world, _ptr(out), 6 * cnt, _ptr(pieces))
     keys = ("split_fronts", "split_member", "factor_bytes", "contrib_bytes", "stage_bytes", "sends", "recvs", "max_ops_level")
-    return dict(zip(keys, (int(v) for v in out))), pieces[:cnt]
+    pieces = pieces[:cnt]
+    pieces = np.column_stack([pieces[:, :5], pieces[:, 5] & 1, pieces[:, 5] >> 1]) if cnt else np.zeros((0, 7), dtype=np.int64)
+    return dict(zip(keys, (int(v) for v in out))), pieces
 
 
 def plan_exchanges(solver: "Solver", rank: int, world: int) -> np.ndarray:

@@ -462,6 +462,11 @@ static void plan_split(NumericTree* nt, bool device) {
    size_t stage = 0;
    long pair_seq = 0;
    std::vector<int> ex_count(std::max(nt->world, 1), 0);
+   int ex_max = EX_MAX_OPS;      // SYLVER_B200_EX_MAX_OPS: tests force small groups
+   {
+      const char* xe = getenv("SYLVER_B200_EX_MAX_OPS");
+      if (xe && atoi(xe) >= 1) ex_max = atoi(xe);
+   }
    for (int l = 0; l < st->nlevels; ++l) {
       ++pair_seq;      // groups never span levels
       std::fill(ex_count.begin(), ex_count.end(), 0);
@@ -490,7 +495,7 @@ static void plan_split(NumericTree* nt, bool device) {
                if (d == src) continue;
                // group id, computed identically on every rank (whether it takes part or not): a new
                // group starts when either end of the pair already has EX_MAX_OPS operations in it
-               if (ex_count[src] >= EX_MAX_OPS || ex_count[d] >= EX_MAX_OPS) {
+               if (ex_count[src] >= ex_max || ex_count[d] >= ex_max) {
                   ++pair_seq;
                   std::fill(ex_count.begin(), ex_count.end(), 0);
                }
@@ -1037,6 +1042,9 @@ static void issue_posdef(NumericTree* nt) {
       // update, its diagonal-block factorization and panel solve run on a second stream beside
       // the rest of the trailing update, taking the latency-bound potrf off the critical path.
       const bool lookahead = nt->stream2 && lp.steps.size() >= 2 && lp.count <= 16;
+      // profiled runs bracket every launch with events: the SAME launches, but the chain of the next
+      // pair is issued on the main stream too, so that a bracket holds the kernel's own time
+      cudaStream_t la_stream = nt->profile ? s : nt->stream2;
       if (nt->pair_updates) {
          // Block columns are factorized in pairs: column si, a rank-nb update of column si+1
          // alone, column si+1 -- then ONE rank-2nb update of everything behind the pair (half as
@@ -1067,7 +1075,7 @@ static void issue_posdef(NumericTree* nt) {
                upd(l1, l1.upd_prefix, l1.upd_tiles, (int)(si / 2), 2 * nb, 0, s);
                chain(si + 2, s);
             } else {
-               cudaStream_t s2 = nt->stream2;
+               cudaStream_t s2 = la_stream;
                upd(l1, l1.upd2n_prefix, l1.upd2n_tiles, (int)(si / 2), 2 * nb, 0, s);
                CU_TRY(cudaEventRecord(nt->ev_next, s));
                CU_TRY(cudaStreamWaitEvent(s2, nt->ev_next, 0));
@@ -1084,7 +1092,7 @@ static void issue_posdef(NumericTree* nt) {
             update(si, 0, s);
          }
       } else {
-         cudaStream_t s2 = nt->stream2;
+         cudaStream_t s2 = la_stream;
          potrf(0, s);
          trsm(0, s);
          for (size_t si = 0; si < lp.steps.size(); ++si) {
@@ -1364,7 +1372,8 @@ void numeric_tree_timings(const NumericTree* nt, double* out4) {
 // communicator).  out8: split fronts in the tree, split fronts this rank works on, factor arena
 // bytes, contribution arena bytes, panel staging bytes, pieces sent, pieces received, largest
 // number of point-to-point operations in one level.  pieces (6 longs each, at most cap/6):
-// level, front (topmost reference node), peer, offset, count (doubles), direction (0 send, 1 recv).
+// level, front (topmost reference node), peer, offset, count (doubles), direction (0 send, 1 recv)
+// + 2 * exchange group id (the NCCL group the operation is issued in, the same on both sides).
 int numeric_plan_split(SymbolicTree* st, int rank, int world, long* out8, int cap, long* pieces) {
    NumericTree nt;
    nt.st = st;
@@ -1390,7 +1399,7 @@ int numeric_plan_split(SymbolicTree* st, int rank, int world, long* out8, int ca
          for (const Piece& x : (dir == 0 ? nt.csends[l] : nt.crecvs[l])) {
             if (6 * cnt + 5 < cap) {
                long* o = pieces + 6 * cnt;
-               o[0] = l; o[1] = st->ref_top[x.f]; o[2] = x.peer; o[3] = x.off; o[4] = (long)x.count; o[5] = dir;
+               o[0] = l; o[1] = st->ref_top[x.f]; o[2] = x.peer; o[3] = x.off; o[4] = (long)x.count; o[5] = dir + 2 * x.seq;
             }
             ++cnt;
          }

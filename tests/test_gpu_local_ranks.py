@@ -146,8 +146,8 @@ def test_delays_cross_rank_boundaries(lib):
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
-@pytest.mark.parametrize("kind,k", [("lap27", 14), ("lap7", 20), ("lap27", 18)])
-def test_split_fronts_match_single_rank(lib, monkeypatch, kind, k, world):
+@pytest.mark.parametrize("kind,k,exmax", [("lap27", 14, 0), ("lap7", 20, 0), ("lap27", 18, 0), ("lap27", 18, 2)])
+def test_split_fronts_match_single_rank(lib, monkeypatch, kind, k, exmax, world):
     """Top-of-tree fronts split over their rank group (block-column cyclic ownership, panel
     broadcasts, contribution blocks gathered tile column by tile column -- SURVEY.md 8e).  The
     threshold is lowered so that the small test trees have split fronts several levels deep,
@@ -157,6 +157,9 @@ def test_split_fronts_match_single_rank(lib, monkeypatch, kind, k, world):
     ref_x = single[0][1]
     be_ref = gen.backward_error(n, ptr, row, val, ref_x, b)
     monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "40")
+    if exmax:
+        # contribution pieces exchanged in many small groups (the fix for the 8-GPU hang, engine.cu)
+        monkeypatch.setenv("SYLVER_B200_EX_MAX_OPS", str(exmax))
     order = _problem(kind, k)[4]
 
     def rank_body(rank, w):

@@ -69,14 +69,16 @@ def test_chain_coarsening_invariants(lib, monkeypatch, kind, k):
     s0.free()
 
 
+@pytest.mark.parametrize("exmax", [400, 2])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("kind,k", [("lap27", 16), ("lap7", 24)])
-def test_split_plan_pairs_up_and_covers(lib, monkeypatch, kind, k, world):
+def test_split_plan_pairs_up_and_covers(lib, monkeypatch, kind, k, world, exmax):
     """Every piece a rank sends is received by its peer at the same level with the same extent,
     in the same order per ordered rank pair (what NCCL's grouped send/recv matching needs), every
     rank that works on a parent front ends up with every piece of each child's block exactly
     once, and the pieces of a block do not overlap."""
     monkeypatch.setenv("SYLVER_B200_SPLIT_MIN", "48")
+    monkeypatch.setenv("SYLVER_B200_EX_MAX_OPS", str(exmax))      # 2: many small exchange groups
     s, n = analysed(kind, k)
     sym = s.symbolic()
     plans = [sb.plan_split(s, r, world) for r in range(world)]
@@ -85,16 +87,30 @@ def test_split_plan_pairs_up_and_covers(lib, monkeypatch, kind, k, world):
     sends = {}
     recvs = {}
     for r, (_, pieces) in enumerate(plans):
-        for (l, f, peer, off, count, d) in pieces.tolist():
+        for (l, f, peer, off, count, d, grp) in pieces.tolist():
             assert peer != r and count > 0 and off >= 0
-            (sends if d == 0 else recvs).setdefault((r, peer) if d == 0 else (peer, r), []).append((l, f, off, count))
+            (sends if d == 0 else recvs).setdefault((r, peer) if d == 0 else (peer, r), []).append((l, f, off, count, grp))
     assert sends.keys() == recvs.keys() and len(sends) > 0
     for pair in sends:
-        assert sends[pair] == recvs[pair], pair          # same order on both sides
+        assert sends[pair] == recvs[pair], pair          # same order AND same exchange group on both sides
+    # exchange groups (one NCCL group each): ids increase along every rank's list, never span
+    # levels, and no rank has more than 400 operations in one (the bound that avoids the 8-GPU hang)
+    for r, (_, pieces) in enumerate(plans):
+        for d in (0, 1):
+            g = pieces[pieces[:, 5] == d][:, 6]
+            assert (np.diff(g) >= 0).all()
+        if len(pieces):
+            ids, cnts = np.unique(pieces[:, 6], return_counts=True)
+            assert cnts.max() <= exmax
+            for i in ids:
+                assert len(set(pieces[pieces[:, 6] == i][:, 0].tolist())) == 1
+    if exmax == 2 and world >= 4:      # some level was cut into several groups
+        allp = np.concatenate([p[1] for p in plans])
+        assert len(np.unique(allp[:, 6])) > len(np.unique(allp[:, 0]))
     # coverage: per (front, destination rank) the received pieces are disjoint intervals
     got = {}
     for (src, dst), lst in recvs.items():
-        for (l, f, off, count) in lst:
+        for (l, f, off, count, grp) in lst:
             got.setdefault((f, dst), []).append((off, off + count, src))
     for (f, dst), iv in got.items():
         iv.sort()
@@ -123,7 +139,7 @@ def test_split_can_be_disabled(lib, monkeypatch):
         d, pieces = sb.plan_split(s, r, 4)
         assert d["split_fronts"] == 0
         # without split fronts every cross-rank edge is one whole-block piece
-        assert all(off == 0 for (_, _, _, off, _, _) in pieces.tolist())
+        assert all(off == 0 for (_, _, _, off, _, _, _) in pieces.tolist())
     s.free()
 
 
@@ -221,7 +237,7 @@ nlev = int(pieces[:, 0].max()) + 1 if len(pieces) else 0
 got = 0
 for l in range(nlev):
     reqs, bufs = [], []
-    for i, (lv, f, peer, off, count, d) in enumerate(pieces.tolist()):
+    for i, (lv, f, peer, off, count, d, grp) in enumerate(pieces.tolist()):
         if lv != l: continue
         # gloo matches by (peer, tag): number the messages of an ordered pair in plan order
         if d == 1:
