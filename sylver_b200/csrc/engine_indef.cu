@@ -73,6 +73,8 @@ void indef_setup(NumericTree* nt) {
    // own opt-in to > 48 KB of dynamic shared memory
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
    CU_TRY(cudaFuncSetAttribute(k_gemm_batched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+   CU_TRY(cudaFuncSetAttribute(k_gemm_diag3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES));
+   CU_TRY(cudaFuncSetAttribute(k_gemm_diag3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
    SymbolicTree* st = nt->st;
    const int N = st->nnodes;
    nt->m.assign(N, 0); nt->n.assign(N, 0); nt->ldl.assign(N, 0); nt->loff.assign(N, 0);
@@ -262,6 +264,8 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
    // device-side rendezvous is used there.
    const bool shared_device = comm().fabric != nullptr;
    const bool legacy = shared_device || (getenv("SYLVER_B200_APTP_LEGACY") && getenv("SYLVER_B200_APTP_LEGACY")[0] == '1');
+   // SYLVER_B200_FUSE_DIAG=0: the 32 x 32 diagonal factorization as a launch of its own (A/B runs)
+   const bool fuse_diag = !(getenv("SYLVER_B200_FUSE_DIAG") && getenv("SYLVER_B200_FUSE_DIAG")[0] == '0');
    long launches = 0;
    for (auto& c : nt->chunks) c.used = 0;
    if (nt->d_xw) { cudaFree(nt->d_xw); cudaFree(nt->d_xwoff); nt->d_xw = nullptr; nt->d_xwoff = nullptr; }
@@ -476,31 +480,43 @@ void run_indef(NumericTree* nt, sylver_inform_c* stats) {
                ++launches;
             }
             int cnt_s = cnt_o;
+            bool diag_done = false;      // the previous block's panel update already factorized this block's diagonal
             for (int ib = 0; ib < OB / IB; ++ib) {
                while (cnt_s > 0 && nt->n[order[cnt_s - 1]] <= o * OB + ib * IB) --cnt_s;
                if (cnt_s == 0) break;
                TileBatch rb{d_fr, d_row, cnt_s};
                TileBatch ub{d_fr, d_inn, cnt_s};
+               // does another block column of this panel follow (for any front)?
+               int cnt_next = cnt_s;
+               while (cnt_next > 0 && nt->n[order[cnt_next - 1]] <= o * OB + (ib + 1) * IB) --cnt_next;
+               const bool fuse_next = fuse_diag && !legacy && ib + 1 < OB / IB && cnt_next > 0;
                {
                   ProfScope ps(nt, KC_POTRF);
-                  // the first block column of a panel also opens it (cnt_s == cnt_o then)
-                  k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small, (ib == 0 && !legacy) ? OB : 0);
+                  if (!diag_done) {
+                     // the first block column of a panel also opens it (cnt_s == cnt_o then)
+                     k_ldlt_diag32<<<cnt_s, 32, 0, s>>>(T, d_fr, d_diag, u, small, (ib == 0 && !legacy) ? OB : 0);
+                     ++launches;
+                  }
                   if (legacy) {
                      k_apply32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
                      k_finish32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, small);
                      k_swap_failed<<<cnt_s, SW_THREADS, 0, s>>>(T, d_fr, d_diag);
-                     launches += 4;
+                     launches += 3;
                   } else {
                      k_block_column32<<<row_prefix[cnt_s], AP_THREADS, 0, s>>>(T, rb, d_diag, u, small);
-                     launches += 2;
+                     ++launches;
                   }
                }
                {
                   // rest of the panel, including the columns that just failed (CTAs of fronts
-                  // with nothing left in the panel exit at once)
+                  // with nothing left in the panel exit at once); fused: + the next diagonal block
                   ProfScope ps(nt, KC_TRSM);
-                  k_gemm_batched<<<gemm_grid(3, inn_prefix[cnt_s]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
+                  if (fuse_next)
+                     k_gemm_diag3<<<gemm_grid(3, inn_prefix[cnt_s]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, d_diag, u, small);
+                  else
+                     k_gemm_batched<<<gemm_grid(3, inn_prefix[cnt_s]), GT_THREADS, GT_SMEM_BYTES, s>>>(T, ub, 3, 0, IB, nullptr, 0, 0, 1);
                   ++launches;
+                  diag_done = fuse_next;
                }
             }
             const bool upd = nt->n[order[0]] > (o + 1) * OB || o > 0;

@@ -535,10 +535,22 @@ __device__ __forceinline__ void gemm_tile_prefetch(const GemmDest& d, int i0, in
 // tile columns tstart, tstart + tstep, ... of the tile grid (look-ahead scheduling: the grid
 // size limits a launch to the first tile column, tstart = 1 skips it; split fronts: the tile
 // columns this rank owns).  Launch gemm_grid(mode, tiles) CTAs.
-static __global__ void __launch_bounds__(GT_THREADS, 2)
-k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld,
-               int tstart, int tstep) {
-   extern __shared__ __align__(128) double smem[];
+// Fused diagonal step (indefinite path, defined in kernels_indef.cuh): the CTA that updates the
+// next 32 x 32 diagonal block of a front factorizes it right away (k_ldlt_diag32's work) instead
+// of a launch of its own after the whole panel update.
+struct DiagScratch;
+struct FusedDiag {
+   char* scratch;            // DiagScratch array of the launch (one per front of the batch)
+   size_t stride;            // sizeof(DiagScratch)
+   double u, small;
+};
+__device__ void ldlt_diag32_front(const DevTree& T, int f, DiagScratch* out, double u, double small, int begin_ob,
+                                  double* S, double* dinv, int* lperm);
+
+template <bool FUSED>
+__device__ __forceinline__ void gemm_body(const DevTree& T, const TileBatch& batch, int mode, int step, int nb,
+                                          const double* __restrict__ W, int wld, int tstart, int tstep,
+                                          const FusedDiag& fd, double* smem) {
    const int half = (mode == 2) ? 0 : (blockIdx.x & 1);
    const int item = (mode == 2) ? blockIdx.x : (blockIdx.x >> 1);
    const int fi = find_front(batch, item);
@@ -605,6 +617,16 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
       const int kbeg = (mode == 3) ? st.kbeg : (mode == 5 ? st.obeg : (mode == 7 ? st.cb[sl] : (mode == 6 ? st.cb[sl] : (step ? 0 : st.nelim1))));
       t.K = (mode == 3) ? st.klen : (mode == 5 ? st.p0 - st.obeg : ((mode == 6 || mode == 7) ? st.ce[sl] - kbeg : st.nelim - kbeg));
       const bool first_pass = contrib && kbeg == 0;
+      // FUSED (mode 3): the CTA of the front's first tile also factorizes the next diagonal block,
+      // whether or not this block column passed any pivot
+      if constexpr (FUSED) {
+         if (local == 0 && half == 0 && !(t.K > 0 && st.oend > st.p0)) {
+            if (threadIdx.x < 32)
+               ldlt_diag32_front(T, f, reinterpret_cast<DiagScratch*>(fd.scratch + fi * fd.stride), fd.u, fd.small, 0, smem,
+                                 smem + 32 * 33, reinterpret_cast<int*>(smem + 32 * 33 + 68));
+            return;
+         }
+      }
       if (t.K == 0 && !(mode == 4 && first_pass)) return;
       const int first = (mode == 3) ? st.p0 : (mode == 5 ? st.oend : (mode == 7 ? st.co[sl] : n));     // first column/row of the updated region
       const int base = first & ~1;
@@ -683,6 +705,24 @@ k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const dou
    if (active) gemm_tile_prefetch(d, i0, j0);
    gemm_tile_mainloop(pipe, t, active, acc);
    if (active) gemm_tile_epilogue(d, i0, j0, acc);
+   if constexpr (FUSED) {
+      // first tile of the front (ti = tj = 0, left half): it holds the next diagonal block
+      // [p0, p0 + 32)^2 entirely; once all warps of this CTA have written their part, warp 0
+      // factorizes it (the pipeline buffers are free by now)
+      if (item == batch.prefix[fi] && half == 0) {
+         __syncthreads();
+         if (threadIdx.x < 32)
+            ldlt_diag32_front(T, f, reinterpret_cast<DiagScratch*>(fd.scratch + fi * fd.stride), fd.u, fd.small, 0, smem,
+                              smem + 32 * 33, reinterpret_cast<int*>(smem + 32 * 33 + 68));
+      }
+   }
+}
+
+static __global__ void __launch_bounds__(GT_THREADS, 2)
+k_gemm_batched(DevTree T, TileBatch batch, int mode, int step, int nb, const double* __restrict__ W, int wld,
+               int tstart, int tstep) {
+   extern __shared__ __align__(128) double smem[];
+   gemm_body<false>(T, batch, mode, step, nb, W, wld, tstart, tstep, FusedDiag{nullptr, 0, 0.0, 0.0}, smem);
 }
 
 // ---------------------------------------------------------------------------

@@ -46,15 +46,10 @@ struct DiagScratch {
 
 // begin_ob > 0: this is the first block column of an outer panel of up to begin_ob candidates
 // (what k_outer_begin did in a launch of its own).
-static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int* __restrict__ fronts,
-                                                           DiagScratch* __restrict__ scratch, double u, double small,
-                                                           int begin_ob) {
-   __shared__ double S[IB * SLD];
-   __shared__ double dinv[2 * IB + 2];
-   __shared__ int lperm[IB];
-   const int f = fronts[blockIdx.x];
+__device__ void ldlt_diag32_front(const DevTree& T, int f, DiagScratch* out, double u, double small, int begin_ob,
+                                  double* S, double* dinv, int* lperm) {
    FrontState& st = T.state[f];
-   const int lane = threadIdx.x;
+   const int lane = threadIdx.x & 31;
    if (begin_ob > 0) {
       if (lane == 0) {
          st.obeg = st.p0;
@@ -197,7 +192,7 @@ static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int*
       p += pivsiz;
    }
    __syncwarp();
-   DiagScratch& o = scratch[blockIdx.x];
+   DiagScratch& o = *out;
 #pragma unroll
    for (int r = 0; r < IB; ++r) o.S[r * SLD + lane] = S[r * SLD + lane];      // coalesced
    o.dinv[2 * lane] = dinv[2 * lane];
@@ -205,6 +200,27 @@ static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int*
    if (lane < 2) o.dinv[2 * IB + lane] = 0.0;
    o.lperm[lane] = lperm[lane];
    if (lane == 0) st.npass = wb;    // the apply kernel lowers this with atomicMin
+}
+
+// begin_ob > 0: this is the first block column of an outer panel of up to begin_ob candidates
+// (what k_outer_begin did in a launch of its own).
+static __global__ void __launch_bounds__(32) k_ldlt_diag32(DevTree T, const int* __restrict__ fronts,
+                                                           DiagScratch* __restrict__ scratch, double u, double small,
+                                                           int begin_ob) {
+   __shared__ double S[IB * SLD];
+   __shared__ double dinv[2 * IB + 2];
+   __shared__ int lperm[IB];
+   ldlt_diag32_front(T, fronts[blockIdx.x], scratch + blockIdx.x, u, small, begin_ob, S, dinv, lperm);
+}
+
+// K = 32 panel update (k_gemm_batched mode 3) whose first CTA per front also factorizes the NEXT
+// diagonal block as soon as it has written it: one launch fewer per block column, and the 45 us
+// of the pivoted 32 x 32 factorization overlap with the rest of the panel update.
+static __global__ void __launch_bounds__(GT_THREADS, 2)
+k_gemm_diag3(DevTree T, TileBatch batch, DiagScratch* __restrict__ scratch, double u, double small) {
+   extern __shared__ __align__(128) double smem[];
+   gemm_body<true>(T, batch, 3, 0, IB, nullptr, 0, 0, 1,
+                   FusedDiag{reinterpret_cast<char*>(scratch), sizeof(DiagScratch), u, small}, smem);
 }
 
 // per-column D^-1 application coefficients: l[j] = cs*w[j] + co*w[partner]
