@@ -546,8 +546,7 @@ static void plan_split(NumericTree* nt, bool device) {
       nt->d_split_fronts = dev_upload(split_fronts);
       nt->d_splitP = dev_upload(nt->splitP);
       nt->d_splitQ = dev_upload(nt->splitQ);
-      nt->stage_doubles = stage;
-      CU_TRY(cudaMalloc(&nt->d_stage, stage * sizeof(double)));
+      nt->stage_doubles = 0;      // panels are broadcast in place: no staging buffer any more
       CU_TRY(cudaMalloc(&nt->d_Wsplit, (size_t)nb * nb * sizeof(double)));
    }
    if (!nt->d_zero) {
